@@ -1,0 +1,57 @@
+// Shared device-side definitions of libpbte_cuda (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "pbte_cuda.h"
+
+namespace pbte_dev
+{
+constexpr int kMaxFaces = PBTE_MAX_FACES;
+constexpr int kMaxDim = 3;
+
+// Device image of the problem plus the sweep state, passed by value to the kernels.
+//
+// HBM layout (all FP64 unless noted):
+//   mass/massT [ne][ms]            ms = ndof*ndof rounded up to an even count (16-byte rows for bulk copies)
+//   stiff      [ne][dim][ms]
+//   fmass/fcoup[ne][F][ms]
+//   fint       [ne][F][ndof]       fnormal [ne][F][3]   ftbc [ne][F]   fnbr int32 [ne][F]   basis [ne][ndof]
+//   flux       [ne][nslots][ndof]  persistent angular flux; slot = (owned direction in schedule-class order) * nband + band,
+//                                  so the slots of one schedule class are contiguous for every element
+//   tc_prev    [ne][ndof]          previous-iteration pseudo-temperature (source of the sweep)
+//   partial    [nclass][1+dim][ne][ndof]   per-class moment partial sums written by the sweep (every entry, every sweep)
+//   mom        [1+dim][ne][ndof]   Tc | Qc_0.. : the vector that is all-reduced across GPUs
+//   slot_*     per-slot scalars: direction (3), v, c1 = nu*C/omega, c2 = nu_max - nu, cb = C/omega, moment factors
+struct DevProblem
+{
+    int dim, ne, n, F, nband, nslots, ms, nclass;
+    double nu_max;
+    const double *mass, *massT, *stiff, *fmass, *fcoup, *fint, *fnormal, *ftbc, *basis;
+    const int32_t *fnbr;
+    const double *slot_dir;  // [nslots][3]
+    const double *slot_v, *slot_c1, *slot_c2, *slot_cb, *slot_mf;  // [nslots]
+    const double *slot_qf;   // [nslots][3]
+    double *flux;
+    const double *tc_prev;
+    double *partial;
+    const int32_t *cls_slot_begin;  // [nclass+1]
+    const uint8_t *cls_out;         // [nclass][ne] faces with n.Omega > 0 for some direction of the class
+    const uint8_t *cls_in;          // [nclass][ne] interior faces with n.Omega < 0 for some direction of the class
+    uint8_t *pivots;                // [ne][nslots][ndof] cached pivot lanes (FullLU policy) or nullptr
+    int32_t *error_flag;            // device int: first PBTE_ERR_* raised by a kernel
+};
+
+// n . Omega with the reference's operation order: sequential sum over d < dim, no FMA contraction
+// (mfem::Vector::operator*, used at src/AngularSweepOrder.cpp:128 and src/PBTESolver.cpp:161,281).
+__device__ __forceinline__ double dot_seq(const double *nrm, const double *omega, int dim)
+{
+    double s = __dmul_rn(nrm[0], omega[0]);
+    if (dim > 1) s = __dadd_rn(s, __dmul_rn(nrm[1], omega[1]));
+    if (dim > 2) s = __dadd_rn(s, __dmul_rn(nrm[2], omega[2]));
+    return s;
+}
+
+}  // namespace pbte_dev

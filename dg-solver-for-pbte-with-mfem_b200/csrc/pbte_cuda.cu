@@ -1,0 +1,1077 @@
+// libpbte_cuda: C ABI of include/pbte_cuda.h.  Host-side orchestration (device image, schedule classes,
+// level lists, CUDA-graph replay of a sweep) around the kernels in schedule.cuh / sweep_*.cuh / moments.cuh.
+#include "pbte_cuda.h"
+
+#include "common.cuh"
+#include "moments.cuh"
+#include "peaks.cuh"
+#include "schedule.cuh"
+#include "sweep_generic.cuh"
+#include "sweep_warp.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace pbte_dev;
+
+namespace
+{
+thread_local std::string g_err = "no error";
+
+int fail(int status, const std::string &msg)
+{
+    g_err = msg;
+    return status;
+}
+
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t ck_e_ = (call);                                                                           \
+        if (ck_e_ != cudaSuccess)                                                                             \
+            return fail(PBTE_ERR_CUDA, std::string(#call) + " failed: " + cudaGetErrorString(ck_e_) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+    } while (0)
+
+template <class T>
+struct DevBuf
+{
+    T *p = nullptr;
+    size_t count = 0;
+    cudaError_t alloc(size_t n)
+    {
+        release();
+        count = n;
+        if (n == 0) return cudaSuccess;
+        return cudaMalloc(&p, n * sizeof(T));
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        count = 0;
+    }
+    ~DevBuf() { release(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+};
+}  // namespace
+
+struct pbte_handle
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int cache_policy = 0, kernel_choice = 0, use_graph = 1;
+
+    // sizes
+    int dim = 0, ne = 0, n = 0, F = 0, ndir = 0, nband = 0, ms = 0;
+    int k0 = 0, k1 = 0;  // owned directions [k0, k1)
+    int nloc() const { return k1 - k0; }
+    int nslots() const { return nloc() * nband; }
+    bool has_topology = false, has_matrices = false, has_bands = false, has_basis = false, has_dirs = false, missing_bc = false;
+    double omega = 0.0, heat_cap_v = 0.0, nu_max = 0.0;
+    std::vector<double> h_dir, h_dirw, h_invkn, h_vg, h_hc, h_fw;
+    std::vector<int32_t> h_fnbr;
+    std::vector<double> h_fnormal;
+
+    // device image
+    DevBuf<double> mass, massT, stiff, fmass, fcoup, fint, fnormal, ftbc, basis, dirs;
+    DevBuf<int32_t> fnbr;
+
+    // schedule
+    bool scheduled = false;
+    int nclass = 0, max_levels = 0;
+    std::vector<int> class_of_dir;         // [nloc]
+    std::vector<int> slotdir_of_dir;       // [nloc] position of the direction in class-major order
+    std::vector<int> cls_slot_begin;       // [nclass+1] (in slots)
+    std::vector<int32_t> h_pass, h_level;  // [nclass][ne]
+    std::vector<int> level_offsets;        // [max_levels+1] into items
+    DevBuf<int2> items;
+    DevBuf<int32_t> d_cls_slot_begin;
+    DevBuf<uint8_t> cls_out, cls_in, pivots;
+    DevBuf<double> slot_dir, slot_v, slot_c1, slot_c2, slot_cb, slot_mf, slot_qf;
+    WarpKernelShape shape{0, 0};
+    int kernel_used = 0;
+    bool pivots_recorded = false;
+
+    // state
+    DevBuf<double> flux, tc_prev, tv_prev, partial, mom, cell, norms, scratch;
+    DevBuf<int32_t> error_flag;
+    double *h_norms = nullptr;  // pinned [4]
+    int32_t *h_flag = nullptr;  // pinned
+    double last_tv_norm = 0.0, last_tc_norm = 0.0;
+
+    // graph replay of one sweep
+    cudaGraphExec_t graph_exec = nullptr;
+    int graph_mode = -1;
+
+    // stats
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    bool sweep_timed = false;
+    int64_t launches = 0, sweeps = 0, launches_per_sweep = 0;
+    double last_sweep_ms = 0.0, last_finish_ms = 0.0;
+
+    ~pbte_handle()
+    {
+        if (graph_exec) cudaGraphExecDestroy(graph_exec);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (ev2) cudaEventDestroy(ev2);
+        if (h_norms) cudaFreeHost(h_norms);
+        if (h_flag) cudaFreeHost(h_flag);
+        if (own_stream && stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace
+{
+struct DeviceGuard
+{
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// upload `count` matrices of n*n doubles with a device stride of ms doubles
+int upload_matrices(DevBuf<double> &dst, const double *src, size_t count, int n, int ms, cudaStream_t st)
+{
+    const size_t nn = (size_t)n * n;
+    CK(dst.alloc(count * ms));
+    if (count == 0) return PBTE_OK;
+    if ((size_t)ms == nn) CK(cudaMemcpyAsync(dst.p, src, count * nn * sizeof(double), cudaMemcpyHostToDevice, st));
+    else
+    {
+        CK(cudaMemsetAsync(dst.p, 0, count * ms * sizeof(double), st));
+        CK(cudaMemcpy2DAsync(dst.p, ms * sizeof(double), src, nn * sizeof(double), nn * sizeof(double), count, cudaMemcpyHostToDevice, st));
+    }
+    return PBTE_OK;
+}
+
+template <class T>
+int upload(DevBuf<T> &dst, const T *src, size_t count, cudaStream_t st)
+{
+    CK(dst.alloc(count));
+    if (count) CK(cudaMemcpyAsync(dst.p, src, count * sizeof(T), cudaMemcpyHostToDevice, st));
+    return PBTE_OK;
+}
+
+DevProblem make_dev_problem(pbte_handle *h)
+{
+    DevProblem P{};
+    P.dim = h->dim;
+    P.ne = h->ne;
+    P.n = h->n;
+    P.F = h->F;
+    P.nband = h->nband;
+    P.nslots = h->nslots();
+    P.ms = h->ms;
+    P.nclass = h->nclass;
+    P.nu_max = h->nu_max;
+    P.mass = h->mass.p;
+    P.massT = h->massT.p;
+    P.stiff = h->stiff.p;
+    P.fmass = h->fmass.p;
+    P.fcoup = h->fcoup.p;
+    P.fint = h->fint.p;
+    P.fnormal = h->fnormal.p;
+    P.ftbc = h->ftbc.p;
+    P.basis = h->basis.p;
+    P.fnbr = h->fnbr.p;
+    P.slot_dir = h->slot_dir.p;
+    P.slot_v = h->slot_v.p;
+    P.slot_c1 = h->slot_c1.p;
+    P.slot_c2 = h->slot_c2.p;
+    P.slot_cb = h->slot_cb.p;
+    P.slot_mf = h->slot_mf.p;
+    P.slot_qf = h->slot_qf.p;
+    P.flux = h->flux.p;
+    P.tc_prev = h->tc_prev.p;
+    P.partial = h->partial.p;
+    P.cls_slot_begin = h->d_cls_slot_begin.p;
+    P.cls_out = h->cls_out.p;
+    P.cls_in = h->cls_in.p;
+    P.pivots = h->pivots.p;
+    P.error_flag = h->error_flag.p;
+    return P;
+}
+
+// ---- warp-kernel dispatch ------------------------------------------------------------------------
+typedef void (*WarpKernelFn)(DevProblem, const int2 *, int, WarpKernelShape);
+
+template <int N, int DIM>
+WarpKernelFn pick_piv(int piv)
+{
+    switch (piv)
+    {
+        case 0: return sweep_warp_kernel<N, DIM, 0>;
+        case 1: return sweep_warp_kernel<N, DIM, 1>;
+        default: return sweep_warp_kernel<N, DIM, 2>;
+    }
+}
+
+WarpKernelFn pick_warp_kernel(int n, int dim, int piv)
+{
+    if (dim == 2)
+    {
+        switch (n)
+        {
+            case 3: return pick_piv<3, 2>(piv);
+            case 4: return pick_piv<4, 2>(piv);
+            case 6: return pick_piv<6, 2>(piv);
+            case 9: return pick_piv<9, 2>(piv);
+            case 10: return pick_piv<10, 2>(piv);
+            case 15: return pick_piv<15, 2>(piv);
+            case 16: return pick_piv<16, 2>(piv);
+            case 25: return pick_piv<25, 2>(piv);
+            default: return nullptr;
+        }
+    }
+    if (dim == 3)
+    {
+        switch (n)
+        {
+            case 4: return pick_piv<4, 3>(piv);
+            case 8: return pick_piv<8, 3>(piv);
+            case 10: return pick_piv<10, 3>(piv);
+            case 20: return pick_piv<20, 3>(piv);
+            case 27: return pick_piv<27, 3>(piv);
+            default: return nullptr;
+        }
+    }
+    return nullptr;
+}
+
+int check_handle(pbte_handle *h)
+{
+    if (!h) return fail(PBTE_ERR_INVALID, "null handle");
+    return PBTE_OK;
+}
+
+// Enqueue the kernels of one sweep on the handle's stream.  piv: 0 search, 1 search+record, 2 replay.
+int enqueue_sweep(pbte_handle *h, int piv, int64_t *launch_count)
+{
+    const DevProblem P = make_dev_problem(h);
+    int64_t launches = 0;
+    if (h->kernel_used == 2)
+    {
+        WarpKernelFn fn = pick_warp_kernel(h->n, h->dim, piv);
+        const size_t smem = sweep_warp_smem(h->n, h->dim, h->shape);
+        for (int L = 0; L < h->max_levels; ++L)
+        {
+            const int begin = h->level_offsets[L], count = h->level_offsets[L + 1] - begin;
+            if (count == 0) continue;
+            fn<<<count, kWarpsPerCta * 32, smem, h->stream>>>(P, h->items.p, begin, h->shape);
+            ++launches;
+        }
+    }
+    else
+    {
+        const size_t smem = sweep_generic_smem(h->n, h->F);
+        for (int L = 0; L < h->max_levels; ++L)
+        {
+            const int begin = h->level_offsets[L], count = h->level_offsets[L + 1] - begin;
+            if (count == 0) continue;
+            sweep_generic_kernel<<<count, 128, smem, h->stream>>>(P, h->items.p, begin);
+            ++launches;
+        }
+    }
+    const size_t count = (size_t)(1 + h->dim) * h->ne * h->n;
+    reduce_partials_kernel<<<(unsigned)((count + 255) / 256), 256, 0, h->stream>>>(count, h->nclass, h->partial.p, h->mom.p);
+    ++launches;
+    CK(cudaGetLastError());
+    if (launch_count) *launch_count = launches;
+    return PBTE_OK;
+}
+
+int run_finalize(pbte_handle *h)
+{
+    int seg = 1;
+    while (seg < h->n && seg < 32) seg <<= 1;
+    const size_t threads = (size_t)(1 + h->dim) * h->ne * seg;
+    finalize_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, h->stream>>>(h->ne, h->n, 1 + h->dim, seg, h->mom.p, h->basis.p, h->cell.p);
+    ++h->launches;
+    CK(cudaGetLastError());
+    return PBTE_OK;
+}
+
+int run_norms(pbte_handle *h, double *diff2, double *tv2, double *tc2)
+{
+    norms_kernel<<<1, 1024, 0, h->stream>>>(h->ne, (size_t)h->ne * h->n, h->cell.p, h->tv_prev.p, h->mom.p, h->norms.p);
+    ++h->launches;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->h_norms, h->norms.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_flag, h->error_flag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *diff2 = h->h_norms[0];
+    *tv2 = h->h_norms[1];
+    *tc2 = h->h_norms[2];
+    return PBTE_OK;
+}
+
+int alloc_moment_state(pbte_handle *h)
+{
+    const size_t block = (size_t)h->ne * h->n, nm = 1 + h->dim;
+    CK(h->mom.alloc(nm * block));
+    CK(h->cell.alloc(nm * h->ne));
+    CK(h->tv_prev.alloc(h->ne));
+    CK(h->tc_prev.alloc(block));
+    CK(h->norms.alloc(4));
+    CK(h->error_flag.alloc(1));
+    CK(cudaMemsetAsync(h->mom.p, 0, nm * block * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->cell.p, 0, nm * h->ne * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->tv_prev.p, 0, h->ne * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->tc_prev.p, 0, block * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->error_flag.p, 0, sizeof(int32_t), h->stream));
+    CK(cudaMallocHost(&h->h_norms, 4 * sizeof(double)));
+    CK(cudaMallocHost(&h->h_flag, sizeof(int32_t)));
+    return PBTE_OK;
+}
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int pbte_cuda_abi_version(void) { return PBTE_ABI_VERSION; }
+const char *pbte_cuda_last_error(void) { return g_err.c_str(); }
+
+int pbte_cuda_device_count(int *count)
+{
+    if (!count) return fail(PBTE_ERR_INVALID, "count is null");
+    int c = 0;
+    const cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess)
+    {
+        *count = 0;
+        return fail(PBTE_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    }
+    *count = c;
+    return PBTE_OK;
+}
+
+void pbte_cuda_default_options(pbte_options_t *opt)
+{
+    if (!opt) return;
+    std::memset(opt, 0, sizeof(*opt));
+    opt->device = -1;
+    opt->use_graph = 1;
+}
+
+int pbte_cuda_create(const pbte_problem_t *p, const pbte_options_t *opt_in, pbte_handle_t **out)
+{
+    if (!p || !out) return fail(PBTE_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (p->abi_version != PBTE_ABI_VERSION) return fail(PBTE_ERR_INVALID, "problem image has a different ABI version");
+    if (p->ne < 0 || p->ndof < 0 || p->ndir < 0 || p->nband < 0 || p->dim < 0 || p->dim > 3 || p->nfaces < 0 || p->nfaces > PBTE_MAX_FACES)
+        return fail(PBTE_ERR_INVALID, "invalid sizes in problem image");
+    pbte_options_t opt;
+    if (opt_in) opt = *opt_in;
+    else pbte_cuda_default_options(&opt);
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(PBTE_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
+    int dev = opt.device;
+    if (dev < 0) CK(cudaGetDevice(&dev));
+    if (dev >= ndev) return fail(PBTE_ERR_INVALID, "device ordinal out of range");
+
+    pbte_handle *h = new (std::nothrow) pbte_handle();
+    if (!h) return fail(PBTE_ERR_NOMEM, "out of host memory");
+    struct Cleanup
+    {
+        pbte_handle *h;
+        ~Cleanup() { delete h; }
+    } cleanup{h};
+    h->device = dev;
+    DeviceGuard guard(dev);
+    if (opt.stream) h->stream = (cudaStream_t)opt.stream;
+    else
+    {
+        CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->own_stream = true;
+    }
+    CK(cudaEventCreate(&h->ev0));
+    CK(cudaEventCreate(&h->ev1));
+    CK(cudaEventCreate(&h->ev2));
+    h->cache_policy = opt.cache_policy;
+    h->kernel_choice = opt.kernel;
+    h->use_graph = opt.use_graph;
+    h->dim = p->dim;
+    h->ne = p->ne;
+    h->n = p->ndof;
+    h->F = p->nfaces;
+    h->ndir = p->ndir;
+    h->nband = p->nband;
+    h->ms = ((p->ndof * p->ndof + 1) / 2) * 2;
+    h->omega = p->omega;
+    h->heat_cap_v = p->heat_cap_v;
+    h->k0 = opt.dir_begin;
+    h->k1 = opt.dir_end;
+    if (h->k0 == 0 && h->k1 == 0) h->k1 = p->ndir;
+    if (h->k0 < 0 || h->k1 > p->ndir || h->k0 > h->k1) return fail(PBTE_ERR_INVALID, "direction range out of bounds");
+
+    const size_t ne = p->ne, F = p->nfaces, n = p->ndof;
+    if (p->dir && p->dir_w && p->ndir > 0)
+    {
+        h->h_dir.assign(p->dir, p->dir + 3 * (size_t)p->ndir);
+        h->h_dirw.assign(p->dir_w, p->dir_w + p->ndir);
+        h->has_dirs = true;
+    }
+    if (p->inv_kn && p->vg && p->heat_cap && p->freq_w && p->nband > 0)
+    {
+        h->h_invkn.assign(p->inv_kn, p->inv_kn + p->nband);
+        h->h_vg.assign(p->vg, p->vg + p->nband);
+        h->h_hc.assign(p->heat_cap, p->heat_cap + p->nband);
+        h->h_fw.assign(p->freq_w, p->freq_w + p->nband);
+        h->nu_max = 0.0;
+        for (double v : h->h_invkn) h->nu_max = std::max(h->nu_max, v);  // dt_inv_ (src/PBTESolver.cpp:39-46)
+        h->has_bands = true;
+    }
+    if (p->face_nbr && p->face_normal && ne > 0 && F > 0)
+    {
+        h->h_fnbr.assign(p->face_nbr, p->face_nbr + ne * F);
+        h->h_fnormal.assign(p->face_normal, p->face_normal + ne * F * 3);
+        for (int32_t v : h->h_fnbr)
+            if (v >= (int32_t)ne || v < PBTE_FACE_NONE) return fail(PBTE_ERR_INVALID, "face_nbr entry out of range");
+        int st = upload(h->fnbr, p->face_nbr, ne * F, h->stream);
+        if (st) return st;
+        st = upload(h->fnormal, p->face_normal, ne * F * 3, h->stream);
+        if (st) return st;
+        h->has_topology = true;
+    }
+    if (p->mass || p->stiff || p->face_mass || p->face_coupling || p->face_integral || p->face_tbc)
+    {
+        if (!(p->mass && p->stiff && p->face_mass && p->face_coupling && p->face_integral && p->face_tbc && h->has_topology && n > 0))
+            return fail(PBTE_ERR_INVALID, "incomplete matrix set in problem image");
+        int st;
+        if ((st = upload_matrices(h->mass, p->mass, ne, (int)n, h->ms, h->stream))) return st;
+        {
+            std::vector<double> mt(ne * n * n);
+            for (size_t e = 0; e < ne; ++e)
+                for (size_t i = 0; i < n; ++i)
+                    for (size_t j = 0; j < n; ++j) mt[e * n * n + i + j * n] = p->mass[e * n * n + j + i * n];
+            if ((st = upload_matrices(h->massT, mt.data(), ne, (int)n, h->ms, h->stream))) return st;
+            CK(cudaStreamSynchronize(h->stream));
+        }
+        if ((st = upload_matrices(h->stiff, p->stiff, ne * p->dim, (int)n, h->ms, h->stream))) return st;
+        if ((st = upload_matrices(h->fmass, p->face_mass, ne * F, (int)n, h->ms, h->stream))) return st;
+        if ((st = upload_matrices(h->fcoup, p->face_coupling, ne * F, (int)n, h->ms, h->stream))) return st;
+        if ((st = upload(h->fint, p->face_integral, ne * F * n, h->stream))) return st;
+        // a boundary face without a wall temperature (NaN) is reported when a sweep is requested
+        if ((st = upload(h->ftbc, p->face_tbc, ne * F, h->stream))) return st;
+        for (size_t i = 0; i < ne * F; ++i)
+            if (p->face_nbr[i] == PBTE_FACE_BOUNDARY && std::isnan(p->face_tbc[i])) h->missing_bc = true;
+        h->has_matrices = true;
+    }
+    if (p->basis_integrals && ne > 0 && n > 0)
+    {
+        int st = upload(h->basis, p->basis_integrals, ne * n, h->stream);
+        if (st) return st;
+        h->has_basis = true;
+    }
+    if (ne > 0 && n > 0)
+    {
+        int st = alloc_moment_state(h);
+        if (st) return st;
+    }
+    if (h->has_matrices && h->has_bands && h->has_dirs)
+    {
+        const size_t fl = ne * (size_t)h->nslots() * n;
+        CK(h->flux.alloc(fl));
+        CK(cudaMemsetAsync(h->flux.p, 0, fl * sizeof(double), h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    cleanup.h = nullptr;
+    *out = h;
+    return PBTE_OK;
+}
+
+int pbte_cuda_destroy(pbte_handle_t *h)
+{
+    if (!h) return PBTE_OK;
+    DeviceGuard guard(h->device);
+    cudaStreamSynchronize(h->stream);
+    delete h;
+    return PBTE_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+int pbte_cuda_build_schedule(pbte_handle_t *h)
+{
+    int st = check_handle(h);
+    if (st) return st;
+    if (!h->has_topology || !h->has_dirs) return fail(PBTE_ERR_STATE, "build_schedule needs face_nbr, face_normal and directions");
+    DeviceGuard guard(h->device);
+    const int ne = h->ne, F = h->F, nloc = h->nloc();
+    h->scheduled = false;
+    if (h->graph_exec)
+    {
+        cudaGraphExecDestroy(h->graph_exec);
+        h->graph_exec = nullptr;
+        h->graph_mode = -1;
+    }
+    if (nloc == 0 || ne == 0)
+    {
+        h->nclass = 0;
+        h->max_levels = 0;
+        h->level_offsets.assign(1, 0);
+        h->scheduled = true;
+        return PBTE_OK;
+    }
+    // 1. upwind masks of every owned direction
+    DevBuf<double> d_dirs;
+    if ((st = upload(d_dirs, h->h_dir.data() + 3 * (size_t)h->k0, 3 * (size_t)nloc, h->stream))) return st;
+    const size_t nm = (size_t)nloc * ne;
+    DevBuf<uint8_t> d_in, d_out, d_bin;
+    CK(d_in.alloc(nm));
+    CK(d_out.alloc(nm));
+    CK(d_bin.alloc(nm));
+    upwind_mask_kernel<<<(unsigned)((nm + 255) / 256), 256, 0, h->stream>>>(ne, F, h->dim, nloc, d_dirs.p, h->fnormal.p, h->fnbr.p, d_in.p,
+                                                                           d_out.p, d_bin.p);
+    ++h->launches;
+    CK(cudaGetLastError());
+    std::vector<uint8_t> in(nm), outm(nm);
+    CK(cudaMemcpyAsync(in.data(), d_in.p, nm, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(outm.data(), d_out.p, nm, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+
+    // 2. directions with identical upwind sets share one DAG -> one schedule class
+    std::map<std::string, int> seen;
+    h->class_of_dir.assign(nloc, -1);
+    std::vector<int> rep;  // representative direction of each class
+    for (int k = 0; k < nloc; ++k)
+    {
+        std::string key(reinterpret_cast<const char *>(in.data() + (size_t)k * ne), ne);
+        auto it = seen.find(key);
+        if (it == seen.end())
+        {
+            it = seen.emplace(std::move(key), (int)rep.size()).first;
+            rep.push_back(k);
+        }
+        h->class_of_dir[k] = it->second;
+    }
+    const int nclass = h->nclass = (int)rep.size();
+    std::vector<int> ndir_in_class(nclass, 0);
+    for (int k = 0; k < nloc; ++k) ++ndir_in_class[h->class_of_dir[k]];
+    h->cls_slot_begin.assign(nclass + 1, 0);
+    for (int c = 0; c < nclass; ++c) h->cls_slot_begin[c + 1] = h->cls_slot_begin[c] + ndir_in_class[c] * std::max(h->nband, 1);
+    {
+        std::vector<int> fill(nclass, 0);
+        h->slotdir_of_dir.assign(nloc, 0);
+        for (int k = 0; k < nloc; ++k)
+        {
+            const int c = h->class_of_dir[k];
+            h->slotdir_of_dir[k] = h->cls_slot_begin[c] / std::max(h->nband, 1) + fill[c]++;
+        }
+    }
+    std::vector<uint8_t> cin((size_t)nclass * ne), cout((size_t)nclass * ne, 0);
+    for (int c = 0; c < nclass; ++c) std::memcpy(cin.data() + (size_t)c * ne, in.data() + (size_t)rep[c] * ne, ne);
+    for (int k = 0; k < nloc; ++k)
+    {
+        uint8_t *dst = cout.data() + (size_t)h->class_of_dir[k] * ne;
+        const uint8_t *src = outm.data() + (size_t)k * ne;
+        for (int e = 0; e < ne; ++e) dst[e] |= src[e];
+    }
+    if ((st = upload(h->cls_in, cin.data(), cin.size(), h->stream))) return st;
+    if ((st = upload(h->cls_out, cout.data(), cout.size(), h->stream))) return st;
+
+    // 3. longest-path relaxation of (pass, level) for every class
+    DevBuf<int32_t> d_pass, d_level, d_changed;
+    const size_t nc = (size_t)nclass * ne;
+    CK(d_pass.alloc(nc));
+    CK(d_level.alloc(nc));
+    CK(d_changed.alloc(1));
+    CK(cudaMemsetAsync(d_pass.p, 0, nc * sizeof(int32_t), h->stream));
+    CK(cudaMemsetAsync(d_level.p, 0, nc * sizeof(int32_t), h->stream));
+    int sweeps_done = 0;
+    const int batch = 8;  // relaxation sweeps between convergence checks
+    for (;;)
+    {
+        CK(cudaMemsetAsync(d_changed.p, 0, sizeof(int32_t), h->stream));
+        for (int b = 0; b < batch; ++b)
+        {
+            relax_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, h->stream>>>(ne, F, nclass, h->cls_in.p, h->fnbr.p, d_pass.p, d_level.p, d_changed.p);
+            ++h->launches;
+        }
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h->h_flag, d_changed.p, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        sweeps_done += batch;
+        if (*h->h_flag == 0) break;
+        // a DAG on ne nodes has no path longer than ne-1 edges: still changing after that means a cycle
+        if (sweeps_done > ne + batch) return fail(PBTE_ERR_SWEEP_STALL, "Angular sweep ordering stalled; check mesh connectivity.");
+    }
+    h->h_pass.resize(nc);
+    h->h_level.resize(nc);
+    CK(cudaMemcpyAsync(h->h_pass.data(), d_pass.p, nc * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_level.data(), d_level.p, nc * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+
+    // 4. work items (class, element) grouped by wavefront level
+    int max_level = 0;
+    for (int32_t l : h->h_level) max_level = std::max(max_level, (int)l);
+    h->max_levels = max_level + 1;
+    h->level_offsets.assign(h->max_levels + 1, 0);
+    for (int32_t l : h->h_level) ++h->level_offsets[l + 1];
+    for (int L = 0; L < h->max_levels; ++L) h->level_offsets[L + 1] += h->level_offsets[L];
+    {
+        std::vector<int> cursor(h->level_offsets.begin(), h->level_offsets.end() - 1);
+        std::vector<int2> items(nc);
+        for (int c = 0; c < nclass; ++c)
+            for (int e = 0; e < ne; ++e) items[cursor[h->h_level[(size_t)c * ne + e]]++] = make_int2(c, e);
+        if ((st = upload(h->items, items.data(), items.size(), h->stream))) return st;
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    {
+        std::vector<int32_t> csb(h->cls_slot_begin.begin(), h->cls_slot_begin.end());
+        if ((st = upload(h->d_cls_slot_begin, csb.data(), csb.size(), h->stream))) return st;
+        CK(cudaStreamSynchronize(h->stream));
+    }
+
+    // 5. sweep tables (only when the image carries matrices and bands)
+    if (h->has_matrices && h->has_bands)
+    {
+        const int ns = h->nslots();
+        std::vector<double> sdir(3 * (size_t)ns), sv(ns), sc1(ns), sc2(ns), scb(ns), smf(ns), sqf(3 * (size_t)ns);
+        for (int k = 0; k < nloc; ++k)
+        {
+            const double *om = &h->h_dir[3 * (size_t)(h->k0 + k)];
+            const double wk = h->h_dirw[h->k0 + k];
+            for (int b = 0; b < h->nband; ++b)
+            {
+                const int s = h->slotdir_of_dir[k] * h->nband + b;
+                const double nu = h->h_invkn[b], v = h->h_vg[b], C = h->h_hc[b], dw = h->h_fw[b];
+                for (int d = 0; d < 3; ++d) sdir[3 * (size_t)s + d] = om[d];
+                sv[s] = v;
+                sc1[s] = nu * C / h->omega;          // invKn * Cwp / omega_      (src/PBTESolver.cpp:270)
+                sc2[s] = h->nu_max - nu;             // dt_inv_ - invKn           (:276)
+                scb[s] = C / h->omega;
+                const double f = nu * wk * dw / h->heat_cap_v;  // (MacroscopicQuantities.cpp:115-118)
+                smf[s] = f;
+                for (int d = 0; d < 3; ++d) sqf[3 * (size_t)s + d] = f * v * om[d];  // (:122-126)
+            }
+        }
+        if ((st = upload(h->slot_dir, sdir.data(), sdir.size(), h->stream))) return st;
+        if ((st = upload(h->slot_v, sv.data(), sv.size(), h->stream))) return st;
+        if ((st = upload(h->slot_c1, sc1.data(), sc1.size(), h->stream))) return st;
+        if ((st = upload(h->slot_c2, sc2.data(), sc2.size(), h->stream))) return st;
+        if ((st = upload(h->slot_cb, scb.data(), scb.size(), h->stream))) return st;
+        if ((st = upload(h->slot_mf, smf.data(), smf.size(), h->stream))) return st;
+        if ((st = upload(h->slot_qf, sqf.data(), sqf.size(), h->stream))) return st;
+        CK(cudaStreamSynchronize(h->stream));
+
+        CK(h->partial.alloc((size_t)nclass * (1 + h->dim) * ne * h->n));
+
+        // kernel choice and its shared-memory shape
+        int nF = 0, nK = 0;
+        for (size_t i = 0; i < cin.size(); ++i)
+        {
+            nF = std::max(nF, __builtin_popcount(cout[i]));
+            nK = std::max(nK, __builtin_popcount(cin[i]));
+        }
+        h->shape = WarpKernelShape{nF, nK};
+        h->kernel_used = 1;
+        if (h->kernel_choice != 1 && pick_warp_kernel(h->n, h->dim, 0) != nullptr)
+        {
+            const size_t smem = sweep_warp_smem(h->n, h->dim, h->shape);
+            int max_optin = 0;
+            CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+            if (smem <= (size_t)max_optin)
+            {
+                for (int piv = 0; piv < 3; ++piv)
+                    CK(cudaFuncSetAttribute(pick_warp_kernel(h->n, h->dim, piv), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                h->kernel_used = 2;
+            }
+        }
+        if (h->kernel_choice == 2 && h->kernel_used != 2) return fail(PBTE_ERR_INVALID, "warp-register kernel not available for this ndof/dim");
+        if (h->kernel_used == 1)
+        {
+            const size_t smem = sweep_generic_smem(h->n, h->F);
+            CK(cudaFuncSetAttribute(sweep_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+        h->pivots.release();
+        h->pivots_recorded = false;
+        if (h->kernel_used == 2 && h->cache_policy == 0) CK(h->pivots.alloc((size_t)ne * ns * h->n));
+    }
+    h->scheduled = true;
+    return PBTE_OK;
+}
+
+int pbte_cuda_schedule_info(pbte_handle_t *h, int32_t *n_classes, int32_t *max_levels)
+{
+    int st = check_handle(h);
+    if (st) return st;
+    if (!h->scheduled) return fail(PBTE_ERR_STATE, "schedule not built");
+    if (n_classes) *n_classes = h->nclass;
+    if (max_levels) *max_levels = h->max_levels;
+    return PBTE_OK;
+}
+
+int pbte_cuda_get_order(pbte_handle_t *h, int32_t k, int32_t *order)
+{
+    int st = check_handle(h);
+    if (st) return st;
+    if (!h->scheduled) return fail(PBTE_ERR_STATE, "schedule not built");
+    if (k < h->k0 || k >= h->k1 || !order) return fail(PBTE_ERR_INVALID, "direction not owned by this handle");
+    // reference list order = elements sorted by (pass, id): counting sort of the device-computed pass numbers
+    const int ne = h->ne;
+    const int32_t *pass = h->h_pass.data() + (size_t)h->class_of_dir[k - h->k0] * ne;
+    int maxp = 0;
+    for (int e = 0; e < ne; ++e) maxp = std::max(maxp, (int)pass[e]);
+    std::vector<int> off(maxp + 2, 0);
+    for (int e = 0; e < ne; ++e) ++off[pass[e] + 1];
+    for (int p = 0; p <= maxp; ++p) off[p + 1] += off[p];
+    for (int e = 0; e < ne; ++e) order[off[pass[e]]++] = e;
+    return PBTE_OK;
+}
+
+int pbte_cuda_get_levels(pbte_handle_t *h, int32_t k, int32_t *level)
+{
+    int st = check_handle(h);
+    if (st) return st;
+    if (!h->scheduled) return fail(PBTE_ERR_STATE, "schedule not built");
+    if (k < h->k0 || k >= h->k1 || !level) return fail(PBTE_ERR_INVALID, "direction not owned by this handle");
+    std::memcpy(level, h->h_level.data() + (size_t)h->class_of_dir[k - h->k0] * h->ne, sizeof(int32_t) * h->ne);
+    return PBTE_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+int pbte_cuda_reset_state(pbte_handle_t *h)
+{
+    int st = check_handle(h);
+    if (st) return st;
+    DeviceGuard guard(h->device);
+    if (h->flux.p) CK(cudaMemsetAsync(h->flux.p, 0, h->flux.count * sizeof(double), h->stream));
+    if (h->mom.p)
+    {
+        CK(cudaMemsetAsync(h->mom.p, 0, h->mom.count * sizeof(double), h->stream));
+        CK(cudaMemsetAsync(h->cell.p, 0, h->cell.count * sizeof(double), h->stream));
+        CK(cudaMemsetAsync(h->tv_prev.p, 0, h->tv_prev.count * sizeof(double), h->stream));
+        CK(cudaMemsetAsync(h->tc_prev.p, 0, h->tc_prev.count * sizeof(double), h->stream));
+        CK(cudaMemsetAsync(h->error_flag.p, 0, sizeof(int32_t), h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return PBTE_OK;
+}
+
+static int coeff_slot(pbte_handle_t *h, int32_t k, int32_t band, int *slot)
+{
+    if (!h->flux.p) return fail(PBTE_ERR_STATE, "handle holds no flux (problem image without matrices/bands)");
+    if (!h->scheduled) return fail(PBTE_ERR_STATE, "schedule not built (flux layout follows the schedule classes)");
+    if (k < h->k0 || k >= h->k1 || band < 0 || band >= h->nband) return fail(PBTE_ERR_INVALID, "coefficient block index out of range");
+    *slot = h->slotdir_of_dir[k - h->k0] * h->nband + band;
+    return PBTE_OK;
+}
+
+int pbte_cuda_upload_coeff(pbte_handle_t *h, int32_t k, int32_t band, const double *host)
+{
+    int st = check_handle(h);
+    if (st) return st;
+    int slot = 0;
+    if ((st = coeff_slot(h, k, band, &slot))) return st;
+    if (!host) return fail(PBTE_ERR_INVALID, "null host pointer");
+    DeviceGuard guard(h->device);
+    const size_t n = h->n;
+    CK(cudaMemcpy2DAsync(h->flux.p + (size_t)slot * n, (size_t)h->nslots() * n * sizeof(double), host, n * sizeof(double), n * sizeof(double),
+                         h->ne, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return PBTE_OK;
+}
+
+int pbte_cuda_download_coeff(pbte_handle_t *h, int32_t k, int32_t band, double *host)
+{
+    int st = check_handle(h);
+    if (st) return st;
+    int slot = 0;
+    if ((st = coeff_slot(h, k, band, &slot))) return st;
+    if (!host) return fail(PBTE_ERR_INVALID, "null host pointer");
+    DeviceGuard guard(h->device);
+    const size_t n = h->n;
+    CK(cudaMemcpy2DAsync(host, n * sizeof(double), h->flux.p + (size_t)slot * n, (size_t)h->nslots() * n * sizeof(double), n * sizeof(double),
+                         h->ne, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return PBTE_OK;
+}
+
+int pbte_cuda_upload_moments(pbte_handle_t *h, const double *Tc, const double *Tv)
+{
+    int st = check_handle(h);
+    if (st) return st;
+    if (!h->mom.p) return fail(PBTE_ERR_STATE, "handle holds no moment state");
+    DeviceGuard guard(h->device);
+    const size_t block = (size_t)h->ne * h->n;
+    if (Tc)
+    {
+        CK(cudaMemcpyAsync(h->tc_prev.p, Tc, block * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->mom.p, Tc, block * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
+    if (Tv)
+    {
+        CK(cudaMemcpyAsync(h->tv_prev.p, Tv, h->ne * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->cell.p, Tv, h->ne * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return PBTE_OK;
+}
+
+int pbte_cuda_download_moments(pbte_handle_t *h, double *Tc, double *Qc, double *Tv, double *Qv)
+{
+    int st = check_handle(h);
+    if (st) return st;
+    if (!h->mom.p) return fail(PBTE_ERR_STATE, "handle holds no moment state");
+    DeviceGuard guard(h->device);
+    const size_t block = (size_t)h->ne * h->n;
+    if (Tc) CK(cudaMemcpyAsync(Tc, h->mom.p, block * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (Qc) CK(cudaMemcpyAsync(Qc, h->mom.p + block, h->dim * block * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (Tv) CK(cudaMemcpyAsync(Tv, h->cell.p, h->ne * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (Qv) CK(cudaMemcpyAsync(Qv, h->cell.p + h->ne, (size_t)h->dim * h->ne * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return PBTE_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+int pbte_cuda_sweep(pbte_handle_t *h)
+{
+    int st = check_handle(h);
+    if (st) return st;
+    if (!h->has_matrices || !h->has_bands) return fail(PBTE_ERR_STATE, "sweep needs the full problem image");
+    if (!h->scheduled) return fail(PBTE_ERR_STATE, "sweep before build_schedule");
+    if (h->missing_bc) return fail(PBTE_ERR_MISSING_BC, "a boundary face has no isothermal wall temperature");
+    DeviceGuard guard(h->device);
+    int piv = 0;
+    if (h->pivots.p) piv = h->pivots_recorded ? 2 : 1;
+    CK(cudaEventRecord(h->ev0, h->stream));
+    int64_t launches = 0;
+    const bool graph_ok = h->use_graph && piv != 1 && h->max_levels > 0;
+    if (graph_ok)
+    {
+        if (!h->graph_exec || h->graph_mode != piv)
+        {
+            if (h->graph_exec)
+            {
+                cudaGraphExecDestroy(h->graph_exec);
+                h->graph_exec = nullptr;
+            }
+            cudaGraph_t graph = nullptr;
+            CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            st = enqueue_sweep(h, piv, &launches);
+            const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+            if (st) return st;
+            if (ce != cudaSuccess) return fail(PBTE_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+            CK(cudaGraphInstantiate(&h->graph_exec, graph, 0));
+            cudaGraphDestroy(graph);
+            h->graph_mode = piv;
+            h->launches_per_sweep = launches;
+            // the capture consumed the event record: re-record on the live stream
+            CK(cudaEventRecord(h->ev0, h->stream));
+        }
+        CK(cudaGraphLaunch(h->graph_exec, h->stream));
+        launches = h->launches_per_sweep;
+    }
+    else
+    {
+        if ((st = enqueue_sweep(h, piv, &launches))) return st;
+        h->launches_per_sweep = launches;
+    }
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->sweep_timed = true;
+    h->launches += launches;
+    ++h->sweeps;
+    if (piv == 1) h->pivots_recorded = true;
+    return PBTE_OK;
+}
+
+int pbte_cuda_moment_buffer(pbte_handle_t *h, double **device_ptr, size_t *count)
+{
+    int st = check_handle(h);
+    if (st) return st;
+    if (!h->mom.p) return fail(PBTE_ERR_STATE, "handle holds no moment state");
+    if (device_ptr) *device_ptr = h->mom.p;
+    if (count) *count = h->mom.count;
+    return PBTE_OK;
+}
+
+int pbte_cuda_finish_iteration(pbte_handle_t *h, double *residual)
+{
+    int st = check_handle(h);
+    if (st) return st;
+    if (!h->mom.p || !h->has_basis) return fail(PBTE_ERR_STATE, "finish_iteration needs basis_integrals in the problem image");
+    DeviceGuard guard(h->device);
+    if ((st = run_finalize(h))) return st;
+    double d2 = 0, t2 = 0, c2 = 0;
+    if ((st = run_norms(h, &d2, &t2, &c2))) return st;
+    // Tv_prev <- Tv, Tc_prev <- Tc   (src/PBTESolver.cpp:328-329)
+    CK(cudaMemcpyAsync(h->tv_prev.p, h->cell.p, h->ne * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->tc_prev.p, h->mom.p, (size_t)h->ne * h->n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaEventRecord(h->ev2, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->sweep_timed)
+    {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_sweep_ms = ms;
+        if (cudaEventElapsedTime(&ms, h->ev1, h->ev2) == cudaSuccess) h->last_finish_ms = ms;
+    }
+    h->last_tv_norm = std::sqrt(t2);
+    h->last_tc_norm = std::sqrt(c2);
+    if (*h->h_flag != 0)
+    {
+        const int flag = *h->h_flag;
+        cudaMemsetAsync(h->error_flag.p, 0, sizeof(int32_t), h->stream);
+        return fail(flag, "a sweep kernel reported a singular local system");
+    }
+    if (!(t2 > 0.0)) return fail(PBTE_ERR_ZERO_NORM, "Tv norm is zero; cannot compute residual.");
+    if (residual) *residual = std::sqrt(d2) / std::sqrt(t2);
+    return PBTE_OK;
+}
+
+int pbte_cuda_last_norms(pbte_handle_t *h, double *tv_norm, double *tc_fnorm)
+{
+    int st = check_handle(h);
+    if (st) return st;
+    if (tv_norm) *tv_norm = h->last_tv_norm;
+    if (tc_fnorm) *tc_fnorm = h->last_tc_norm;
+    return PBTE_OK;
+}
+
+int pbte_cuda_solve(pbte_handle_t *h, int32_t max_iter, double tol, int32_t *iters_done, double *residual, double *history)
+{
+    int st = check_handle(h);
+    if (st) return st;
+    double res = 0.0;
+    int it = 0;
+    for (; it < max_iter;)
+    {
+        if ((st = pbte_cuda_sweep(h))) return st;
+        if ((st = pbte_cuda_finish_iteration(h, &res))) return st;
+        if (history) history[it] = res;
+        ++it;
+        if (res < tol) break;
+    }
+    if (iters_done) *iters_done = it;
+    if (residual) *residual = res;
+    return PBTE_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+int pbte_cuda_macro_reset(pbte_handle_t *h)
+{
+    int st = check_handle(h);
+    if (st) return st;
+    if (!h->mom.p) return fail(PBTE_ERR_STATE, "handle holds no moment state");
+    DeviceGuard guard(h->device);
+    CK(cudaMemsetAsync(h->mom.p, 0, h->mom.count * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->cell.p, 0, h->cell.count * sizeof(double), h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return PBTE_OK;
+}
+
+int pbte_cuda_macro_accumulate(pbte_handle_t *h, int32_t k, int32_t band, const double *coeff)
+{
+    int st = check_handle(h);
+    if (st) return st;
+    if (!h->mom.p || !h->has_bands || !h->has_dirs) return fail(PBTE_ERR_STATE, "macro_accumulate needs directions and band tables");
+    if (k < 0 || k >= h->ndir || band < 0 || band >= h->nband || !coeff) return fail(PBTE_ERR_INVALID, "macro_accumulate: index out of range");
+    DeviceGuard guard(h->device);
+    const size_t block = (size_t)h->ne * h->n;
+    if (h->scratch.count < block) CK(h->scratch.alloc(block));
+    CK(cudaMemcpyAsync(h->scratch.p, coeff, block * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    const double f = h->h_invkn[band] * h->h_dirw[k] * h->h_fw[band] / h->heat_cap_v;
+    const double *om = &h->h_dir[3 * (size_t)k];
+    const double v = h->h_vg[band];
+    accumulate_block_kernel<<<(unsigned)((block + 255) / 256), 256, 0, h->stream>>>(block, h->dim, f, f * v * om[0], f * v * om[1], f * v * om[2],
+                                                                                   h->scratch.p, h->mom.p);
+    ++h->launches;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    return PBTE_OK;
+}
+
+int pbte_cuda_macro_finalize(pbte_handle_t *h, const double *basis)
+{
+    int st = check_handle(h);
+    if (st) return st;
+    if (!h->mom.p) return fail(PBTE_ERR_STATE, "handle holds no moment state");
+    DeviceGuard guard(h->device);
+    if (basis)
+    {
+        if ((st = upload(h->basis, basis, (size_t)h->ne * h->n, h->stream))) return st;
+        h->has_basis = true;
+    }
+    if (!h->has_basis) return fail(PBTE_ERR_STATE, "macro_finalize needs basis_integrals");
+    if ((st = run_finalize(h))) return st;
+    CK(cudaStreamSynchronize(h->stream));
+    return PBTE_OK;
+}
+
+int pbte_cuda_macro_residual(pbte_handle_t *h, const double *prev_tv, double *residual)
+{
+    int st = check_handle(h);
+    if (st) return st;
+    if (!h->mom.p || !prev_tv || !residual) return fail(PBTE_ERR_INVALID, "macro_residual: bad arguments");
+    DeviceGuard guard(h->device);
+    // cell[0] (= Tv) is compared against the caller's vector; tv_prev is the staging buffer
+    DevBuf<double> saved;
+    CK(saved.alloc(h->ne));
+    CK(cudaMemcpyAsync(saved.p, h->tv_prev.p, h->ne * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->tv_prev.p, prev_tv, h->ne * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    double d2 = 0, t2 = 0, c2 = 0;
+    st = run_norms(h, &d2, &t2, &c2);
+    CK(cudaMemcpyAsync(h->tv_prev.p, saved.p, h->ne * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (st) return st;
+    if (!(t2 > 0.0)) return fail(PBTE_ERR_ZERO_NORM, "Tv norm is zero; cannot compute residual.");
+    *residual = std::sqrt(d2) / std::sqrt(t2);
+    return PBTE_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+int pbte_cuda_get_stats(pbte_handle_t *h, pbte_stats_t *s)
+{
+    int st = check_handle(h);
+    if (st) return st;
+    if (!s) return fail(PBTE_ERR_INVALID, "null stats");
+    std::memset(s, 0, sizeof(*s));
+    s->kernel_launches = h->launches;
+    s->sweeps = h->sweeps;
+    s->last_sweep_ms = h->last_sweep_ms;
+    s->last_finish_ms = h->last_finish_ms;
+    s->flux_bytes = (int64_t)(h->flux.count * sizeof(double));
+    s->launches_per_sweep = h->launches_per_sweep;
+    s->kernel_used = h->kernel_used;
+    s->n_classes = h->nclass;
+    s->max_levels = h->max_levels;
+    return PBTE_OK;
+}
+
+int pbte_cuda_get_stream(pbte_handle_t *h, void **stream)
+{
+    int st = check_handle(h);
+    if (st) return st;
+    if (stream) *stream = (void *)h->stream;
+    return PBTE_OK;
+}
+
+int pbte_cuda_measure_peaks(int device, double *fp64_fma_tflops, double *fp64_mma_tflops, double *hbm_copy_gbs)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(PBTE_ERR_CUDA, "no CUDA device available");
+    if (device < 0) CK(cudaGetDevice(&device));
+    DeviceGuard guard(device);
+    const cudaError_t e = measure_peaks(fp64_fma_tflops, fp64_mma_tflops, hbm_copy_gbs);
+    if (e != cudaSuccess) return fail(PBTE_ERR_CUDA, std::string("measure_peaks: ") + cudaGetErrorString(e));
+    return PBTE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,190 @@
+/*
+ * pbte_cuda.h — C ABI of the B200-native PBTE sweep library (libpbte_cuda.so).
+ *
+ * This is the drop-in boundary for the reference's hot path.  The reference has no FFI of its own:
+ * its boundary is the C++ class API that src/PhononBTE.cpp:385-398 calls.  The kept host classes
+ * (pbte::PBTESolver, pbte::AngularSweepOrder, pbte::MacroscopicQuantities — see
+ * dg-solver-for-pbte-with-mfem_b200/host/) flatten their inputs into the POD "problem image" below
+ * and call these entry points; nothing but plain pointers, sizes and status codes crosses the boundary.
+ *
+ * Every array is FP64 / int32, matrices are column-major (entry (i,j) at [i + j*ndof]) exactly like
+ * mfem::DenseMatrix, indices are 0-based.  All functions return PBTE_OK (0) or a negative status;
+ * pbte_cuda_last_error() gives the message of the last failure on the calling thread.
+ * There is no CPU fallback: every compute entry point fails with PBTE_ERR_CUDA when no device is usable.
+ *
+ * Replaces (reference file:line)                                         entry point
+ *   AngularSweepOrder::Build           src/AngularSweepOrder.cpp:78-147  pbte_cuda_build_schedule
+ *   AngularSweepOrder::Order           include/AngularSweepOrder.hpp:28  pbte_cuda_get_order
+ *   PBTESolver::PBTESolver (BuildCellData, AssembleA, LU policy)
+ *                                      src/PBTESolver.cpp:10-206         pbte_cuda_create
+ *   PBTESolver::CreateInitialCoefficients  src/PBTESolver.cpp:76-95      pbte_cuda_reset_state
+ *   PBTESolver::Solve                  src/PBTESolver.cpp:208-332        pbte_cuda_solve
+ *     one pass of its k/b/s/element loop  :238-312                       pbte_cuda_sweep
+ *   MacroscopicQuantities::Reset / AccumulateDirectionalCoeff
+ *                                      src/MacroscopicQuantities.cpp:93-128   (fused into pbte_cuda_sweep)
+ *   MacroscopicQuantities::Finalize / Residual  :130-166                 pbte_cuda_finish_iteration
+ *   accessors Tc/Tv/Qc/Qv              include/MacroscopicQuantities.hpp:67-70   pbte_cuda_download_moments
+ *   coeff[k][b][s] in/out of Solve     src/PBTESolver.cpp:208,252,308    pbte_cuda_upload_coeff / download_coeff
+ */
+#ifndef PBTE_CUDA_H
+#define PBTE_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBTE_ABI_VERSION 1
+#define PBTE_MAX_FACES 8 /* local faces per element (tri 3, quad 4, tet 4, hex 6) */
+
+enum pbte_status
+{
+    PBTE_OK = 0,
+    PBTE_ERR_INVALID = -1,      /* bad argument / size mismatch         (MFEM_VERIFY in the reference)        */
+    PBTE_ERR_CUDA = -2,         /* CUDA runtime failure or no device                                           */
+    PBTE_ERR_SWEEP_STALL = -3,  /* cyclic upwind dependency             (std::runtime_error, AngularSweepOrder.cpp:138-142) */
+    PBTE_ERR_MISSING_BC = -4,   /* boundary face without a temperature  (std::out_of_range, PBTESolver.cpp:287)   */
+    PBTE_ERR_ZERO_NORM = -5,    /* ||Tv|| == 0 in the residual          (MFEM_VERIFY, MacroscopicQuantities.cpp:162) */
+    PBTE_ERR_SINGULAR = -6,     /* zero pivot in a local system                                                */
+    PBTE_ERR_NOMEM = -7,
+    PBTE_ERR_STATE = -8         /* call order violated (e.g. sweep before build_schedule)                      */
+};
+
+/* face_nbr special values */
+#define PBTE_FACE_BOUNDARY (-1) /* isothermal wall; face_tbc holds its temperature */
+#define PBTE_FACE_NONE (-2)     /* padding slot (element has fewer than nfaces faces) */
+
+/*
+ * Problem image: everything PBTESolver's constructor receives, flattened.
+ * Element-local faces are in the order of ElementIntegralData::face_couplings (ascending global face id,
+ * src/ElementIntegrator.cpp:118-257).  Per-element strides: ndof*ndof for matrices, ndof for vectors.
+ */
+typedef struct pbte_problem
+{
+    int32_t abi_version; /* PBTE_ABI_VERSION */
+    int32_t dim;         /* mesh dimension = number of stiffness matrices and of direction components used */
+    int32_t ne;          /* elements */
+    int32_t ndof;        /* local degrees of freedom n */
+    int32_t nfaces;      /* face slots per element F (<= PBTE_MAX_FACES) */
+    int32_t ndir;        /* directions N_a */
+    int32_t nband;       /* bands N_b = nbranch * nspec, band = branch*nspec + spec */
+    int32_t reserved0;
+
+    const double *basis_integrals; /* [ne][ndof]            ElementIntegralData::basis_integrals     */
+    const double *mass;            /* [ne][ndof*ndof]       ::mass_matrix                            */
+    const double *stiff;           /* [ne][dim][ndof*ndof]  ::stiffness_matrices                     */
+    const double *face_mass;       /* [ne][F][ndof*ndof]    ::face_mass_matrices                     */
+    const double *face_coupling;   /* [ne][F][ndof*ndof]    FaceCoupling::coupling (interior faces)  */
+    const double *face_integral;   /* [ne][F][ndof]         FaceCoupling::isothermal_rhs (boundary)  */
+    const double *face_normal;     /* [ne][F][3]            utils::ComputeOutwardFaceNormal          */
+    const int32_t *face_nbr;       /* [ne][F]  neighbour element, PBTE_FACE_BOUNDARY or PBTE_FACE_NONE */
+    const double *face_tbc;        /* [ne][F]  wall temperature iso_bc_.at(attr) for boundary faces  */
+
+    const double *dir;     /* [ndir][3]  AngleDirection::direction */
+    const double *dir_w;   /* [ndir]     AngleDirection::weight    */
+    double omega;          /* AngleQuadrature::TotalWeight()       */
+
+    const double *inv_kn;   /* [nband] PhononProperties::InvKn          (nu)    */
+    const double *vg;       /* [nband] ::GroupVelocity                  (v)     */
+    const double *heat_cap; /* [nband] ::HeatCapacity                   (C)     */
+    const double *freq_w;   /* [nband] ::FrequencyWeight                (Delta) */
+    double heat_cap_v;      /* ::avgHeatCapacity()                      (C_V)   */
+} pbte_problem_t;
+
+typedef struct pbte_options
+{
+    int32_t device;     /* CUDA device ordinal; -1 = current device                                  */
+    int32_t dir_begin;  /* this handle sweeps directions [dir_begin, dir_end); 0,0 = all             */
+    int32_t dir_end;    /*   (the (angle,band) partition of SURVEY §8e: one handle per GPU)          */
+    int32_t cache_policy; /* 0 = FullLU (cache pivot sequences, CachePolicy::FullLU), 1 = OnTheFly    */
+    int32_t kernel;     /* 0 = auto, 1 = generic shared-memory kernel, 2 = warp-register kernel      */
+    int32_t use_graph;  /* 1 = replay the per-iteration launch sequence as a CUDA graph (default), 0 = plain launches */
+    void *stream;       /* cudaStream_t to run on; NULL = a stream owned by the handle               */
+    int32_t reserved[8];
+} pbte_options_t;
+
+typedef struct pbte_handle pbte_handle_t;
+
+/* ---- life cycle -------------------------------------------------------------------------------- */
+int pbte_cuda_abi_version(void);
+const char *pbte_cuda_last_error(void);
+int pbte_cuda_device_count(int *count);
+void pbte_cuda_default_options(pbte_options_t *opt);
+/* Copies the problem image to the device (the caller may free its arrays afterwards). */
+int pbte_cuda_create(const pbte_problem_t *problem, const pbte_options_t *opt, pbte_handle_t **out);
+int pbte_cuda_destroy(pbte_handle_t *h);
+
+/* ---- AngularSweepOrder ------------------------------------------------------------------------- */
+/* Upwind DAG of every owned direction -> pass numbers (reference list order) and wavefront levels,
+ * computed on the device; PBTE_ERR_SWEEP_STALL on a cyclic dependency. */
+int pbte_cuda_build_schedule(pbte_handle_t *h);
+/* order[ne] = AngularSweepOrder::Order(k), bit-exact.  k is a global direction index owned by h. */
+int pbte_cuda_get_order(pbte_handle_t *h, int32_t k, int32_t *order);
+/* level[ne] = wavefront level of every element for direction k (the GPU execution schedule). */
+int pbte_cuda_get_levels(pbte_handle_t *h, int32_t k, int32_t *level);
+/* number of distinct upwind DAGs among the owned directions and the longest level count */
+int pbte_cuda_schedule_info(pbte_handle_t *h, int32_t *n_classes, int32_t *max_levels);
+
+/* ---- state (warm start in, results out) --------------------------------------------------------- */
+/* coeff = 0, Tc = Tv = 0: PBTESolver::CreateInitialCoefficients + MacroscopicQuantities::Reset. */
+int pbte_cuda_reset_state(pbte_handle_t *h);
+/* One block coeff[k][band] as an (ndof x ne) column-major matrix, host memory. */
+int pbte_cuda_upload_coeff(pbte_handle_t *h, int32_t k, int32_t band, const double *host);
+int pbte_cuda_download_coeff(pbte_handle_t *h, int32_t k, int32_t band, double *host);
+/* Previous-iteration moments used as the source of the next sweep (macro.Tc()/macro.Tv() on entry). */
+int pbte_cuda_upload_moments(pbte_handle_t *h, const double *Tc /*[ndof*ne]*/, const double *Tv /*[ne]*/);
+/* Tc [ndof*ne], Qc [dim][ndof*ne], Tv [ne], Qv [dim][ne]; any pointer may be NULL. */
+int pbte_cuda_download_moments(pbte_handle_t *h, double *Tc, double *Qc, double *Tv, double *Qv);
+
+/* ---- iteration --------------------------------------------------------------------------------- */
+/* One pass of the (k, band, element) loop over the owned directions.  Leaves this handle's PARTIAL
+ * moment vector [Tc | Qc_0 .. Qc_{dim-1}] ((1+dim)*ndof*ne doubles, element-major [e][i]) in device memory. */
+int pbte_cuda_sweep(pbte_handle_t *h);
+/* Device pointer / length of the partial moment vector: multi-GPU callers all-reduce (sum) it in place
+ * between pbte_cuda_sweep and pbte_cuda_finish_iteration (one collective per iteration). */
+int pbte_cuda_moment_buffer(pbte_handle_t *h, double **device_ptr, size_t *count);
+/* Finalize (Tv, Qv), residual ||Tv - Tv_prev|| / ||Tv||, then Tv_prev <- Tv, Tc_prev <- Tc. */
+int pbte_cuda_finish_iteration(pbte_handle_t *h, double *residual);
+/* PBTESolver::Solve on one device: up to max_iter iterations, stops when residual < tol.
+ * residual_history (may be NULL) receives one value per executed iteration. */
+int pbte_cuda_solve(pbte_handle_t *h, int32_t max_iter, double tol, int32_t *iters_done, double *residual,
+                    double *residual_history);
+
+/* ||Tv||_2 and ||Tc||_F of the last finish_iteration (the two norms the reference prints per iteration,
+ * src/PBTESolver.cpp:318-326). */
+int pbte_cuda_last_norms(pbte_handle_t *h, double *tv_norm, double *tc_fnorm);
+
+/* ---- stand-alone MacroscopicQuantities calls (outside Solve) ------------------------------------ */
+/* These need only sizes, directions and band tables in the problem image (matrix pointers may be NULL). */
+int pbte_cuda_macro_reset(pbte_handle_t *h);                                                   /* ::Reset                      :93-102  */
+int pbte_cuda_macro_accumulate(pbte_handle_t *h, int32_t k, int32_t band, const double *coeff); /* ::AccumulateDirectionalCoeff :104-128; coeff = host (ndof x ne) */
+int pbte_cuda_macro_finalize(pbte_handle_t *h, const double *basis_integrals /*[ne][ndof] host or NULL*/); /* ::Finalize :130-157 */
+int pbte_cuda_macro_residual(pbte_handle_t *h, const double *prev_tv /*[ne] host*/, double *residual);     /* ::Residual :159-166 */
+
+/* ---- introspection for benchmarks --------------------------------------------------------------- */
+typedef struct pbte_stats
+{
+    int64_t kernel_launches;  /* launches of this library's kernels since create                      */
+    int64_t sweeps;           /* completed pbte_cuda_sweep calls                                       */
+    double last_sweep_ms;     /* device time of the last sweep (CUDA events on the handle's stream)    */
+    double last_finish_ms;    /* device time of the last finish_iteration                              */
+    int64_t flux_bytes;       /* bytes of persistent angular flux held by this handle                  */
+    int64_t launches_per_sweep;
+    int32_t kernel_used;      /* 1 generic, 2 warp-register                                            */
+    int32_t n_classes;
+    int32_t max_levels;
+    int32_t reserved;
+} pbte_stats_t;
+int pbte_cuda_get_stats(pbte_handle_t *h, pbte_stats_t *stats);
+/* The cudaStream_t the handle launches on (for CUDA-event timing by the caller). */
+int pbte_cuda_get_stream(pbte_handle_t *h, void **stream);
+/* Micro-benchmarks for the roofline denominators MEASURED_PEAKS.json lacks: FP64 FMA pipe, FP64 tensor pipe
+ * (DMMA m8n8k4) in TFLOP/s and a plain device copy in GB/s (read+write).  Any pointer may be NULL. */
+int pbte_cuda_measure_peaks(int device, double *fp64_fma_tflops, double *fp64_mma_tflops, double *hbm_copy_gbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBTE_CUDA_H */
