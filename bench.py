@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the PBTE sweep: DOF*angle*band updates per second per source iteration.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1], SURVEY §8d "C2"): builtin unit-cube-hex 4x4x4 refined twice (4096 hexes), DG order 2
+(ndof 27), 8 Gauss polar x 16 uniform azimuth directions (128), "gray" = num_spectral 1 (2 bands), walls -0.5 / top +0.5,
+local matrices as the reference assembles them.  One step = one source iteration: upwind sweeps of every (direction, band)
+over the mesh, fused moments, [all-reduce of the moment vector for N > 1], cell integrals + residual.
+N > 1 (torchrun, one process per GPU): every rank sweeps its own block of directions over the whole mesh; the azimuth count
+grows with N (16*N), so per-GPU work is fixed ("weak" scaling) and the one NCCL all-reduce per iteration is the only
+data-path collective.
+
+Timed with CUDA events on the sweep stream, barrier + synchronize on both sides, max over ranks.  The flux (226 MB per
+128 directions) and the matrix image (0.4 GB) together exceed the 126 MB L2 every step, so no explicit flush is needed.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "dg-solver-for-pbte-with-mfem_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "DOF*angle*band updates/s per sweep"
+UNIT = "updates/s"
+BC3 = {1: -0.5, 2: -0.5, 3: -0.5, 4: -0.5, 5: -0.5, 6: 0.5}
+WORKLOAD = dict(mesh="unit-cube-hex", order=2, refine=2, angle_dim=3, polar=8, azimuth=16, num_spectral=1)
+SAMPLE = dict(WORKLOAD, refine=1)  # CPU legs: same workload one refinement level down (512 hexes), updates/s is size independent
+
+
+def flops_per_update(n, dim, faces):
+    """Algorithmic FP64 flops per update: LU + assembly + source/coupling products + triangular solves, per dof."""
+    f_in = f_out = faces / 2.0
+    per_solve = (2.0 / 3.0) * n ** 3 + 2.0 * (1 + dim + f_out) * n * n + (4 + 2 * f_in) * n * n
+    return per_solve / n
+
+
+def load_measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)), "MEASURED_PEAKS.json"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (recipe of B200_PROFILING.md)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation (its unmodified sources against the MFEM stand-in,
+    oracle/_ref), serial as the reference is; falls back to the C port when oracle/_ref is absent."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc
+    import pbte_b200 as pb
+    mat = dict(pb.SI_MATERIAL)
+    mat["num_spectral"] = SAMPLE["num_spectral"]
+    azim = SAMPLE["azimuth"]  # the sample keeps 128 directions whatever N is
+    times = []
+    if orc.ref_available():
+        kind, cores = "reference", 1
+        rc = orc.RefCase(SAMPLE["mesh"], SAMPLE["order"], SAMPLE["refine"], SAMPLE["angle_dim"], SAMPLE["polar"], azim, True, False, BC3, mat)
+        U = rc.ndof * rc.ne * rc.ndir * rc.nband
+        rs = orc.RefSolver(rc, 1, 0)
+        ctor = rs.ctor_seconds
+        for i in range(args.warmup + args.steps):
+            _, secs = rs.solve()
+            if i >= args.warmup:
+                times.append(secs)
+        sizes = rc.sizes
+    else:
+        kind, cores = "port", os.cpu_count() or 1
+        hc = pb.HostCase(SAMPLE["mesh"], SAMPLE["order"], SAMPLE["refine"], SAMPLE["angle_dim"], SAMPLE["polar"], azim, True, False, BC3,
+                         num_spectral=SAMPLE["num_spectral"])
+        P = hc.problem
+        U = P.updates_per_sweep
+        ctor = 0.0
+        state = None
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            r = orc.solve(P, 1, 0.0, cache_lu=False, threads=cores, **(state or {}))
+            secs = time.perf_counter() - t0
+            state = dict(coeff=r["coeff"], Tc=r["Tc"], Tv=r["Tv"])
+            if i >= args.warmup:
+                times.append(secs)
+        sizes = P
+    t = float(np.mean(times))
+    value = U / t
+    sample = (f"{SAMPLE['mesh']} refine {SAMPLE['refine']} ({sizes.ne} hexes), order 2, {sizes.ndir} directions, {sizes.nband} bands: "
+              f"{U} updates per step; PBTESolver::Solve only (constructor with its LU cache took {ctor:.1f} s, not timed)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C2: unit-cube-hex refine 2 (4096 hexes), order 2, 8x16 directions, 2 bands (gray SMRT); CPU arm runs the bounded sample below"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_baseline_leg(budget_s=25.0):
+    """Rank 0, N = 1: the reference CPU path on a bounded sample, timed beside the GPU numbers."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc
+    import pbte_b200 as pb
+    mat = dict(pb.SI_MATERIAL)
+    mat["num_spectral"] = SAMPLE["num_spectral"]
+    out = {}
+    if orc.ref_available():
+        rc = orc.RefCase(SAMPLE["mesh"], SAMPLE["order"], SAMPLE["refine"], SAMPLE["angle_dim"], SAMPLE["polar"], SAMPLE["azimuth"], True, False, BC3, mat)
+        U = rc.ndof * rc.ne * rc.ndir * rc.nband
+        rs = orc.RefSolver(rc, 1, 0)
+        times = []
+        t_start = time.perf_counter()
+        while len(times) < 4 and time.perf_counter() - t_start < budget_s:
+            times.append(rs.solve()[1])
+        t = float(np.mean(times[1:] if len(times) > 1 else times))
+        out = {"value": U / t, "unit": UNIT, "cores": 1, "kind": "reference",
+               "sample": f"reference sources (-O2) on {SAMPLE['mesh']} refine {SAMPLE['refine']} ({rc.ne} hexes), order 2, {rc.ndir} directions, {rc.nband} bands; "
+                         f"{len(times)} Solve iterations of {U} updates, FullLU cache built once in {rs.ctor_seconds:.1f} s (not timed); MPI path: n/a (dead code in the reference)"}
+        rs.close()
+        rc.close()
+    # labelled extra: the C port threaded over (direction, band) on all host cores
+    hc = pb.HostCase(SAMPLE["mesh"], SAMPLE["order"], SAMPLE["refine"], SAMPLE["angle_dim"], SAMPLE["polar"], SAMPLE["azimuth"], True, False, BC3,
+                     num_spectral=SAMPLE["num_spectral"])
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    orc.solve(hc.problem, 2, 0.0, cache_lu=False, threads=cores)
+    tp = (time.perf_counter() - t0) / 2
+    port = {"value": hc.problem.updates_per_sweep / tp, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "C restatement, LU on the fly, (direction,band) sweeps on all host cores, same sample mesh, 2 iterations"}
+    hc.close()
+    if not out:
+        out = port
+    else:
+        out["threaded_port"] = port
+    return out
+
+
+def run_gpu(args, rank, world, local_rank):
+    import torch
+    import pbte_b200 as pb
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+
+    azim = WORKLOAD["azimuth"] * world
+    hc = pb.HostCase(WORKLOAD["mesh"], WORKLOAD["order"], WORKLOAD["refine"], WORKLOAD["angle_dim"], WORKLOAD["polar"], azim, True, False, BC3,
+                     num_spectral=WORKLOAD["num_spectral"])
+    P = hc.problem
+    k0, k1 = pb.partition_directions(P.ndir, world, rank)
+    stream = torch.cuda.Stream(device=local_rank)
+    solver = pb.Solver(P, device=local_rank, dir_range=(k0, k1), cache_policy=0, stream=stream.cuda_stream)
+    nclass, nlev = solver.build_schedule()
+    ptr, count = solver.moment_buffer()
+    # the moment vector as a torch tensor over the library's device buffer: what NCCL all-reduces in place
+    mom = None
+    if world > 1:
+        class _Buf:
+            __cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 3, "strides": None}
+        mom = torch.as_tensor(_Buf(), device=torch.device("cuda", local_rank))
+
+    def step():
+        solver.sweep()
+        if mom is not None:
+            with torch.cuda.stream(stream):
+                dist.all_reduce(mom, op=dist.ReduceOp.SUM)
+        return solver.finish_iteration()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for _ in range(max(args.warmup, 3)):
+            step()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        st0 = solver.stats()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sweep_ms = []
+        ev0.record(stream)
+        for _ in range(args.steps):
+            res = step()
+            sweep_ms.append(solver.stats().last_sweep_ms)
+        ev1.record(stream)
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        st1 = solver.stats()
+    total_ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    U = P.updates_per_sweep  # all ranks together
+    value = U * args.steps / (total_ms * 1e-3)
+
+    # ---- end-to-end leg: the same iteration with HOST buffers for what crosses the boundary every step ------------
+    #   in : previous-iteration moments Tc, Tv from pinned host memory  (pbte_cuda_upload_moments)
+    #   out: Tc, Qc, Tv, Qv and the residual back to host               (pbte_cuda_download_moments)
+    # The flux is solver state and stays on the device, as in a Solve call of many iterations.
+    block = P.ndof * P.ne
+    tc_host = torch.zeros(block, dtype=torch.float64).pin_memory()
+    tv_host = torch.zeros(P.ne, dtype=torch.float64).pin_memory()
+    m = solver.download_moments()
+    tc_host.copy_(torch.from_numpy(m["Tc"]))
+    tv_host.copy_(torch.from_numpy(m["Tv"]))
+    barrier()
+    t0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        for _ in range(args.steps):
+            solver.upload_moments(tc_host.numpy(), tv_host.numpy())
+            res = step()
+            m = solver.download_moments()
+            tc_host.copy_(torch.from_numpy(m["Tc"]))
+            tv_host.copy_(torch.from_numpy(m["Tv"]))
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = U * args.steps / float(te.item())
+    h2d = (block + P.ne) * 8
+    d2h = ((1 + P.dim) * block + (1 + P.dim) * P.ne + 1) * 8
+
+    # ---- the kept C++ API call, PBTESolver::Solve(coeff, macro), with its full host-state upload/download (N = 1 only) --
+    solve_call = None
+    if world == 1:
+        solver.close()
+        hs = pb.HostSolver(hc, 0)
+        hs.solve(1)
+        t0 = time.perf_counter()
+        _, iters, dev_ms = hs.solve(args.steps)
+        dt = time.perf_counter() - t0
+        solve_call = {"value": U * iters / dt, "unit": UNIT, "iterations_per_call": iters, "seconds": dt, "device_ms": dev_ms,
+                      "h2d_bytes_per_call": P.ndir * P.nband * block * 8 + h2d, "d2h_bytes_per_call": P.ndir * P.nband * block * 8 + d2h,
+                      "note": "one Solve(coeff, macro) call on host DenseMatrix blocks: flux uploaded at entry and downloaded at exit (pageable memory)"}
+        hs.close()
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_src = load_measured_peaks()
+    live = pb.measure_peaks(local_rank)
+    fpu = flops_per_update(P.ndof, P.dim, P.nfaces)
+    U_rank = P.ndof * P.ne * (k1 - k0) * P.nband
+    sweep_s = float(np.mean(sweep_ms)) * 1e-3
+    achieved_tf = fpu * U_rank / sweep_s / 1e12
+    fp64_peak = max(live["fp64_fma_tflops"], live["fp64_mma_tflops"])
+    hbm_gbs = 16.0 * U_rank / sweep_s / 1e9
+    launches = int(st1.kernel_launches - st0.kernel_launches)
+    prof = os.path.join(ROOT, "profiles", "r01_c2_ncu_summary.json")
+    traffic = None
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("dram_bytes_per_sweep")
+        except Exception:
+            traffic = None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C2: builtin unit-cube-hex refine 2 ({P.ne} hexes), DG order 2 (ndof {P.ndof}), 8 Gauss polar x {azim} uniform azimuth = {P.ndir} directions"
+                               f" ({k1 - k0} per GPU), gray SMRT = 2 bands, reference-compatible local matrices; {U} updates per step",
+                   "parallelism": f"directions partitioned over {world} GPU(s), one FP64 all-reduce of [Tc|Qc] per step" if world > 1 else "single GPU",
+                   "l2_flush": "none needed: flux (226 MB per GPU) + matrix image (0.4 GB) exceed the 126 MB L2 every step",
+                   "schedule": {"classes": nclass, "wavefront_levels": nlev, "kernel": "warp-register" if st1.kernel_used == 2 else "generic",
+                                "cuda_graph": True, "pivot_cache": "FullLU policy: pivot lanes cached, LU recomputed in registers"},
+                   "residual_after_run": res},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "what": "per step: Tc,Tv uploaded from pinned host memory, sweep+finish through the C ABI, Tc,Qc,Tv,Qv,residual downloaded; flux stays device resident",
+                "solve_call": solve_call},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak, "traffic": traffic,
+                     "note": f"dominant kernel = sweep_warp_kernel<27,3> ({nlev} wavefront launches per step, {sweep_s * 1e3:.3f} ms per step by CUDA events on the sweep stream);"
+                             f" algorithmic {fpu:.0f} flop/update (SURVEY 8d) x {U_rank} updates; peak = FP64 pipe measured live by pbte_cuda_measure_peaks"
+                             f" (DFMA {live['fp64_fma_tflops']:.1f}, DMMA {live['fp64_mma_tflops']:.1f} TFLOP/s)",
+                     "hbm": {"achieved": hbm_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "frac": hbm_gbs / peaks.get("hbm_gbs"),
+                             "algorithmic_bytes_per_update": 16, "peak_source": peak_src, "live_copy_gbs": live["hbm_copy_gbs"]}},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_baseline_leg()
+        except Exception as ex:  # the CPU leg must never take the GPU numbers down with it
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # convenience: re-launch under torchrun, one process per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", "29531", os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+        sys.exit(subprocess.call(cmd))
+    run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -42,6 +42,12 @@ public:
     double Solve(CoefficientBlocks &coeff, MacroscopicQuantities &macro);
     CoefficientBlocks CreateInitialCoefficients() const;
 
+    /// Extension: change tolerance / iteration cap between Solve calls (the reference fixes them at construction).
+    void SetIterationControl(double tol, int max_iter)
+    {
+        tol_ = tol;
+        max_iter_ = max_iter;
+    }
     /// Device time of the sweeps of the last Solve (ms) and their count; DOF*angle*band updates per sweep.
     double LastSolveSweepMs() const { return sweep_ms_; }
     int LastSolveIterations() const { return iters_; }

@@ -10,6 +10,8 @@
 #include "SpatialMesh.hpp"
 
 #include <cstring>
+#include <iostream>
+#include <sstream>
 #include <string>
 
 namespace
@@ -24,6 +26,16 @@ struct pbte_host_case
     pbte::PhononProperties props;
     std::vector<pbte::ElementIntegralData> elem_data;
     pbte::ProblemImage image;
+};
+
+struct pbte_host_solver
+{
+    pbte_host_case *c;
+    std::unique_ptr<pbte::MacroscopicQuantities> macro;
+    std::unique_ptr<pbte::AngularSweepOrder> sweep;
+    std::unique_ptr<pbte::PBTESolver> solver;
+    pbte::PBTESolver::CoefficientBlocks coeff;
+    int policy = 0;
 };
 
 #define HOST_TRY try {
@@ -167,6 +179,61 @@ int pbte_host_case_solve(pbte_host_case_t *c, int32_t max_iter, double tol, int3
     return PBTE_OK;
     HOST_CATCH
 }
+
+int pbte_host_solver_create(pbte_host_case_t *c, int32_t cache_policy, pbte_host_solver_t **out)
+{
+    if (!c || !out) return PBTE_ERR_INVALID;
+    mfem::set_error_action(mfem::MFEM_ERROR_THROW);
+    HOST_TRY
+    auto s = std::make_unique<pbte_host_solver>();
+    s->c = c;
+    s->policy = cache_policy;
+    s->macro = std::make_unique<pbte::MacroscopicQuantities>(c->spatial.FESpace(), c->props, c->quad);
+    s->sweep = std::make_unique<pbte::AngularSweepOrder>(pbte::AngularSweepOrder::Build(c->spatial.Mesh(), c->quad));
+    s->solver = std::make_unique<pbte::PBTESolver>(c->spatial.Mesh(), c->spatial.FESpace(), c->quad, *s->sweep, c->elem_data, c->props,
+                                                   c->spatial.IsothermalBoundaryTemps(),
+                                                   cache_policy == 0 ? pbte::CachePolicy::FullLU : pbte::CachePolicy::OnTheFly, 0.0, 1);
+    s->coeff = s->solver->CreateInitialCoefficients();
+    *out = s.release();
+    return PBTE_OK;
+    HOST_CATCH
+}
+
+int pbte_host_solver_solve(pbte_host_solver_t *s, int32_t max_iter, double tol, double *residual, int32_t *iters, double *device_ms)
+{
+    if (!s) return PBTE_ERR_INVALID;
+    HOST_TRY
+    s->solver->SetIterationControl(tol, max_iter);
+    std::ostringstream sink;  // the per-iteration log lines of Solve are not part of the measurement
+    std::streambuf *old = std::cout.rdbuf(sink.rdbuf());
+    double res = 0.0;
+    try
+    {
+        res = s->solver->Solve(s->coeff, *s->macro);
+    }
+    catch (...)
+    {
+        std::cout.rdbuf(old);
+        throw;
+    }
+    std::cout.rdbuf(old);
+    if (residual) *residual = res;
+    if (iters) *iters = s->solver->LastSolveIterations();
+    if (device_ms) *device_ms = s->solver->LastSolveSweepMs();
+    return PBTE_OK;
+    HOST_CATCH
+}
+
+int pbte_host_solver_moments(pbte_host_solver_t *s, double *Tc, double *Tv)
+{
+    if (!s) return PBTE_ERR_INVALID;
+    const size_t block = static_cast<size_t>(s->macro->Tc().Height()) * s->macro->Tc().Width();
+    if (Tc) std::memcpy(Tc, s->macro->Tc().Data(), sizeof(double) * block);
+    if (Tv) std::memcpy(Tv, s->macro->Tv().GetData(), sizeof(double) * s->macro->Tv().Size());
+    return PBTE_OK;
+}
+
+void pbte_host_solver_destroy(pbte_host_solver_t *s) { delete s; }
 
 int pbte_host_case_macro(pbte_host_case_t *c, const double *coeff, const double *prev_tv, double *Tc, double *Qc, double *Tv, double *Qv,
                          double *residual)

@@ -47,6 +47,14 @@ PBTE_HOST_API int pbte_host_case_band_table(const pbte_host_case_t *c, int which
  * cache_policy 0 FullLU / 1 OnTheFly. */
 PBTE_HOST_API int pbte_host_case_solve(pbte_host_case_t *c, int32_t max_iter, double tol, int32_t cache_policy, double *residual, int32_t *iters,
                          double *Tc, double *Qc, double *Tv, double *Qv, int32_t *orders, double *coeff);
+/* Persistent solver objects for repeated Solve calls (bench.py end-to-end leg): construction = AngularSweepOrder::Build +
+ * PBTESolver constructor; each solve call is PBTESolver::Solve(coeff, macro) on HOST coefficient blocks (uploaded at entry,
+ * downloaded at exit, src/PBTESolver.cpp:208-332) continuing from the state the previous call returned. */
+typedef struct pbte_host_solver pbte_host_solver_t;
+PBTE_HOST_API int pbte_host_solver_create(pbte_host_case_t *c, int32_t cache_policy, pbte_host_solver_t **out);
+PBTE_HOST_API int pbte_host_solver_solve(pbte_host_solver_t *s, int32_t max_iter, double tol, double *residual, int32_t *iters, double *device_ms);
+PBTE_HOST_API int pbte_host_solver_moments(pbte_host_solver_t *s, double *Tc, double *Tv);
+PBTE_HOST_API void pbte_host_solver_destroy(pbte_host_solver_t *s);
 /* MacroscopicQuantities stand-alone API on host coefficient blocks: Reset, Accumulate (all k,band), Finalize,
  * Residual(prev_Tv).  coeff layout as above. */
 PBTE_HOST_API int pbte_host_case_macro(pbte_host_case_t *c, const double *coeff, const double *prev_tv, double *Tc, double *Qc, double *Tv, double *Qv,

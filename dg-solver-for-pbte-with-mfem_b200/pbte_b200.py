@@ -132,6 +132,10 @@ def host_lib():
                                              c_double_p, c_double_p, c_double_p, c_int32_p, c_double_p]
         lib.pbte_host_case_macro.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]
         lib.pbte_host_case_vertex_values.argtypes = [C.c_void_p, c_double_p, c_double_p, c_int32_p]
+        lib.pbte_host_solver_create.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
+        lib.pbte_host_solver_solve.argtypes = [C.c_void_p, C.c_int32, C.c_double, c_double_p, c_int32_p, c_double_p]
+        lib.pbte_host_solver_moments.argtypes = [C.c_void_p, c_double_p, c_double_p]
+        lib.pbte_host_solver_destroy.argtypes = [C.c_void_p]
         _host = lib
     return _host
 
@@ -284,6 +288,42 @@ class HostCase:
         return out.reshape(-1)[: p.ne * nv.value].reshape(p.ne, nv.value)
 
 
+class HostSolver:
+    """The kept C++ objects (AngularSweepOrder, PBTESolver, MacroscopicQuantities, host coefficient blocks) kept alive across
+    Solve calls; each solve() is PBTESolver::Solve(coeff, macro) with host buffers in and out."""
+
+    def __init__(self, case, cache_policy=0):
+        self.case = case
+        self._h = C.c_void_p()
+        st = host_lib().pbte_host_solver_create(case._h, cache_policy, C.byref(self._h))
+        if st != PBTE_OK:
+            raise PbteError(st, host_lib().pbte_host_last_error().decode())
+
+    def solve(self, max_iter, tol=0.0):
+        res, it, ms = C.c_double(0), C.c_int32(0), C.c_double(0)
+        st = host_lib().pbte_host_solver_solve(self._h, max_iter, tol, C.byref(res), C.byref(it), C.byref(ms))
+        if st != PBTE_OK:
+            raise PbteError(st, host_lib().pbte_host_last_error().decode())
+        return res.value, it.value, ms.value
+
+    def moments(self):
+        p = self.case.problem
+        Tc, Tv = np.zeros(p.ndof * p.ne), np.zeros(p.ne)
+        host_lib().pbte_host_solver_moments(self._h, _dp(Tc), _dp(Tv))
+        return Tc, Tv
+
+    def close(self):
+        if self._h:
+            host_lib().pbte_host_solver_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Solver:
     """One device handle of the C ABI (pbte_cuda_create .. pbte_cuda_destroy)."""
 
@@ -419,3 +459,11 @@ def device_count():
     n = C.c_int(0)
     st = cuda_lib().pbte_cuda_device_count(C.byref(n))
     return n.value if st == PBTE_OK else 0
+
+
+def partition_directions(ndir, world_size, rank):
+    """Contiguous block of directions owned by `rank` (the (angle, band) space is split by direction blocks so
+    that the bands of a direction stay on one GPU).  Blocks differ by at most one direction; trailing ranks may be empty."""
+    base, extra = divmod(ndir, world_size)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)

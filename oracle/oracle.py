@@ -238,3 +238,30 @@ class RefCase:
             raise err
         out.update(coeff=coeff, residual=res.value, seconds_ctor=secs[0], seconds_solve=secs[1])
         return out
+
+
+class RefSolver:
+    """The reference's PBTESolver kept alive across Solve calls (constructor incl. its LU cache timed separately)."""
+
+    def __init__(self, case, iters_per_call=1, policy=0):
+        self.case = case
+        self._h = C.c_void_p()
+        secs = C.c_double(0)
+        with _chdir(case._tmp.name):
+            rc = ref_lib().ref_solver_create(case._h, iters_per_call, policy, C.byref(self._h), C.byref(secs))
+        if rc != 0:
+            raise RuntimeError(f"ref_solver_create: {ref_lib().ref_last_error().decode()}")
+        self.ctor_seconds = secs.value
+
+    def solve(self):
+        res, secs = C.c_double(0), C.c_double(0)
+        with _chdir(self.case._tmp.name):
+            rc = ref_lib().ref_solver_solve(self._h, C.byref(res), C.byref(secs))
+        if rc != 0:
+            raise RuntimeError(f"ref_solver_solve: {ref_lib().ref_last_error().decode()}")
+        return res.value, secs.value
+
+    def close(self):
+        if self._h:
+            ref_lib().ref_solver_destroy(self._h)
+            self._h = C.c_void_p()

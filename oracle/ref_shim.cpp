@@ -230,4 +230,50 @@ REF_API int ref_case_solve(ref_case *c, int max_iter, double tol, int policy, do
     return 0;
     REF_CATCH
 }
+
+// Persistent reference solver for timing: the constructor (LU cache of every (dir,band,cell), src/PBTESolver.cpp:50-73) runs once,
+// then Solve(coeff, macro) is called repeatedly with max_iter fixed at construction, continuing from the returned state.
+struct ref_solver
+{
+    ref_case *c;
+    std::unique_ptr<pbte::MacroscopicQuantities> macro;
+    std::unique_ptr<pbte::AngularSweepOrder> sweep;
+    std::unique_ptr<pbte::PBTESolver> solver;
+    std::vector<std::vector<std::vector<mfem::DenseMatrix>>> coeff;
+};
+
+REF_API int ref_solver_create(ref_case *c, int iters_per_call, int policy, ref_solver **out, double *ctor_seconds)
+{
+    mfem::set_error_action(mfem::MFEM_ERROR_THROW);
+    Silence quiet;
+    REF_TRY
+    auto s = std::make_unique<ref_solver>();
+    s->c = c;
+    const auto t0 = std::chrono::steady_clock::now();
+    s->macro = std::make_unique<pbte::MacroscopicQuantities>(c->spatial.FESpace(), c->props, c->quad);
+    s->macro->Reset();
+    s->sweep = std::make_unique<pbte::AngularSweepOrder>(pbte::AngularSweepOrder::Build(c->spatial.Mesh(), c->quad));
+    s->solver = std::make_unique<pbte::PBTESolver>(c->spatial.Mesh(), c->spatial.FESpace(), c->quad, *s->sweep, c->elem_data, c->props,
+                                                   c->spatial.IsothermalBoundaryTemps(),
+                                                   policy == 0 ? pbte::CachePolicy::FullLU : pbte::CachePolicy::OnTheFly, 0.0, iters_per_call);
+    s->coeff = s->solver->CreateInitialCoefficients();
+    if (ctor_seconds) *ctor_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    *out = s.release();
+    return 0;
+    REF_CATCH
+}
+
+REF_API int ref_solver_solve(ref_solver *s, double *residual, double *seconds)
+{
+    Silence quiet;
+    REF_TRY
+    const auto t0 = std::chrono::steady_clock::now();
+    const double res = s->solver->Solve(s->coeff, *s->macro);
+    if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (residual) *residual = res;
+    return 0;
+    REF_CATCH
+}
+
+REF_API void ref_solver_destroy(ref_solver *s) { delete s; }
 }  // extern "C"

@@ -1,0 +1,263 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the same inputs and
+against the committed golden fixtures generated from the reference's own code.
+
+Bars: sweep schedules bit-exact; Tc / Qc / flux within 1e-10 relative (FP64) per iteration for the cases whose local
+systems are well conditioned.  Three cases are run with the reference's default face rule on
+high-order quads/hexes, where the source iteration itself is unstable (residuals grow, local systems are nearly
+singular); there every FP64 implementation that does not replay the reference's exact operation order differs at
+cond(A)*eps, the tolerance is stated per case, and the same cases are ALSO run with consistent face traces at 1e-10.
+"""
+import numpy as np
+import pytest
+
+import oracle as orc
+import pbte_b200 as pb
+from cases import CASES, host_case
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+TOL = {name: 1e-10 for name in CASES}
+TOL.update(quad_p4=1e-5, hex_p3=1e-8)  # ill-conditioned under quirk Q1, see module docstring
+ALL = ["c0_default", "c1_tri_p1", "tri_p3_si", "quad_p2", "quad_p4", "tet_p1", "tet_p2", "hex_p1", "c2_hex_p2_small", "hex_p3", "quad_p1_dim3"]
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def gpu_solve(P, iters, **kw):
+    s = pb.Solver(P, **kw)
+    info = s.build_schedule()
+    it, res, hist = s.solve(iters, 0.0)
+    out = s.download_moments()
+    out.update(coeff=s.download_all_coeff(), residuals=hist, info=info, stats=s.stats(),
+               orders=np.stack([s.order(k) for k in range(*s.dir_range)]) if P.ndir else None)
+    s.close()
+    return out
+
+
+@pytest.mark.parametrize("name", ALL)
+@pytest.mark.parametrize("kernel,policy", [(0, 0), (0, 1), (1, 1)])
+def test_cuda_matches_oracle(name, kernel, policy):
+    if name == "c0_default" and kernel == 1:
+        pytest.skip("101 iterations of the generic kernel are covered by the shorter cases")
+    hc = host_case(name)
+    P = hc.problem
+    iters = CASES[name]["iters"]
+    want = orc.solve(P, iters, 0.0, cache_lu=True, threads=8)
+    got = gpu_solve(P, iters, kernel=kernel, cache_policy=policy)
+    assert np.array_equal(got["orders"], orc.sweep_orders(P))  # bit-exact schedules
+    tol = TOL[name]
+    for k in ("Tc", "Qc", "Tv", "Qv", "coeff"):
+        assert rel(got[k], want[k]) <= tol, (k, rel(got[k], want[k]))
+    assert np.allclose(got["residuals"], want["residuals"], rtol=max(tol * 10, 1e-9), atol=0)
+    if kernel == 0 and P.ndof <= 32:
+        assert got["stats"].kernel_used == 2  # the warp-register kernel is the one that ran
+    hc.close()
+
+
+@pytest.mark.parametrize("name", ["quad_p4", "hex_p3", "c2_hex_p2_small", "tet_p2"])
+def test_cuda_matches_oracle_consistent_traces(name):
+    """Same meshes with consistent face integrals (well-conditioned systems): 1e-10 at every iteration."""
+    hc = host_case(name, face_rule=1)
+    P = hc.problem
+    s = pb.Solver(P)
+    s.build_schedule()
+    coeff = np.zeros((P.ndir, P.nband, P.ndof * P.ne))
+    Tc, Tv = np.zeros(P.ndof * P.ne), np.zeros(P.ne)
+    for it in range(3):
+        want = orc.solve(P, 1, 0.0, cache_lu=False, threads=8, coeff=coeff, Tc=Tc, Tv=Tv)  # one iteration from the same state
+        s.sweep()
+        r = s.finish_iteration()
+        m = s.download_moments()
+        assert rel(m["Tc"], want["Tc"]) <= 1e-10 and rel(m["Qc"], want["Qc"]) <= 1e-10
+        assert abs(r - want["residual"]) <= 1e-9 * want["residual"]
+        coeff, Tc, Tv = want["coeff"], want["Tc"], want["Tv"]
+    assert rel(s.download_all_coeff(), coeff) <= 1e-10
+    s.close()
+    hc.close()
+
+
+@pytest.mark.parametrize("name", ["c0_default", "c1_tri_p1", "quad_p2", "tet_p1", "hex_p1", "tri_p3_si", "quad_p1_dim3"])
+def test_cuda_matches_reference_golden(name):
+    """Directly against what the reference's own code produced (tests/golden/<case>.npz)."""
+    g = golden(name)
+    hc = host_case(name)
+    got = gpu_solve(hc.problem, CASES[name]["iters"])
+    assert np.array_equal(got["orders"], g["orders"])
+    for k in ("Tc", "Qc", "Tv", "Qv"):
+        assert rel(got[k], g[k].reshape(got[k].shape)) <= 1e-10, k
+    if "coeff" in g.files:
+        assert rel(got["coeff"], g["coeff"]) <= 1e-10
+    assert abs(got["residuals"][-1] - float(g["residual"])) <= 1e-9 * float(g["residual"])
+    hc.close()
+
+
+def test_shipped_golden_default_run():
+    """Known answer shipped by the reference: vertex temperatures of the default run after 101 iterations (full FP64),
+    and the 576 sweep orders of the refined mesh."""
+    s = golden("shipped_default")
+    hc = host_case("c0_default")
+    got = gpu_solve(hc.problem, 101)
+    T_vert = hc.vertex_values(got["Tc"]).reshape(-1)
+    assert np.abs(T_vert - s["vtu_T"]).max() <= 1e-11 * np.abs(s["vtu_T"]).max()
+    assert np.array_equal(got["orders"], s["sweep_dim2"])
+    hc.close()
+    hc = host_case("c0_refined_dim3")
+    sv = pb.Solver(hc.problem)
+    nclass, _ = sv.build_schedule()
+    assert nclass == 6
+    assert np.array_equal(np.stack([sv.order(k) for k in range(576)]), s["sweep_dim3"])
+    sv.close()
+    hc.close()
+
+
+@pytest.mark.parametrize("name", ["c1_tri_p1", "hex_p1"])
+def test_kept_cpp_api_end_to_end(name):
+    """AngularSweepOrder::Build + PBTESolver(...) + Solve(coeff, macro) of the host layer, as the driver calls them."""
+    hc = host_case(name)
+    P = hc.problem
+    iters = CASES[name]["iters"]
+    want = orc.solve(P, iters, 0.0)
+    got = hc.solve(iters, 0.0, cache_policy=0, want_coeff=True)
+    assert got["iters"] == iters
+    assert np.array_equal(got["orders"], orc.sweep_orders(P))
+    for k in ("Tc", "Qc", "Tv", "Qv", "coeff"):
+        assert rel(got[k], want[k]) <= 1e-10, k
+    assert abs(got["residual"] - want["residual"]) <= 1e-9 * want["residual"]
+    # tolerance stop: res < tol ends the loop (src/PBTESolver.cpp:327)
+    loose = hc.solve(50, 0.7)
+    assert loose["iters"] < 50 and loose["residual"] < 0.7
+    hc.close()
+
+
+def test_macroscopic_quantities_standalone_api():
+    """Reset / AccumulateDirectionalCoeff / Finalize / Residual outside Solve."""
+    hc = host_case("quad_p2")
+    P = hc.problem
+    rng = np.random.default_rng(7)
+    coeff = rng.standard_normal((P.ndir, P.nband, P.ndof * P.ne))
+    prev = rng.standard_normal(P.ne) * 1e-14
+    want = orc.moments(P, coeff)
+    got = hc.macro(coeff, prev)
+    for k in ("Tc", "Qc", "Tv", "Qv"):
+        assert rel(got[k], want[k]) <= 1e-12, k
+    assert abs(got["residual"] - orc.residual(want["Tv"], prev)) <= 1e-12
+    hc.close()
+
+
+def test_warm_start_continues_the_iteration():
+    hc = host_case("tet_p1")
+    P = hc.problem
+    a = orc.solve(P, 2, 0.0)
+    b = orc.solve(P, 2, 0.0, coeff=a["coeff"], Tc=a["Tc"], Tv=a["Tv"])
+    s = pb.Solver(P)
+    s.build_schedule()
+    for k in range(P.ndir):
+        for band in range(P.nband):
+            s.upload_coeff(k, band, a["coeff"][k, band])
+    s.upload_moments(a["Tc"], a["Tv"])
+    _, res, hist = s.solve(2, 0.0)
+    m = s.download_moments()
+    assert rel(m["Tc"], b["Tc"]) <= 1e-10 and rel(s.download_all_coeff(), b["coeff"]) <= 1e-10
+    assert np.allclose(hist, b["residuals"], rtol=1e-9)
+    s.close()
+    hc.close()
+
+
+def test_direction_partition_sums_to_the_full_moments():
+    """Two handles sweeping disjoint direction blocks: the sum of their partial moment vectors is the full one
+    (the single all-reduce of the multi-GPU path)."""
+    hc = host_case("hex_p1")
+    P = hc.problem
+    full = pb.Solver(P)
+    full.build_schedule()
+    full.sweep()
+    full.finish_iteration()
+    want = full.download_moments()
+    parts = []
+    for r in range(3):
+        k0, k1 = pb.partition_directions(P.ndir, 3, r)
+        s = pb.Solver(P, dir_range=(k0, k1))
+        s.build_schedule()
+        s.sweep()
+        ptr, count = s.moment_buffer()
+        assert count == (1 + P.dim) * P.ndof * P.ne
+        # read the partial buffer back through finish_iteration-free download
+        parts.append(s.download_moments())
+        for k in range(k0, k1):
+            assert np.array_equal(s.order(k), full.order(k))
+        s.close()
+    tc = sum(p["Tc"] for p in parts)
+    qc = sum(p["Qc"] for p in parts)
+    assert rel(tc, want["Tc"]) <= 1e-13 and rel(qc, want["Qc"]) <= 1e-13
+    full.close()
+    hc.close()
+
+
+def test_empty_direction_block_is_legal():
+    hc = host_case("c1_tri_p1")
+    s = pb.Solver(hc.problem, dir_range=(5, 5))
+    assert s.build_schedule() == (0, 0)
+    s.sweep()
+    assert not s.download_moments()["Tc"].any()
+    s.close()
+    hc.close()
+
+
+def test_missing_boundary_temperature_status():
+    hc = host_case("c1_tri_p1", bcs={1: -0.5, 2: -0.5, 3: 0.5})
+    s = pb.Solver(hc.problem)
+    s.build_schedule()
+    with pytest.raises(pb.PbteError) as ei:
+        s.sweep()
+    assert ei.value.status == -4
+    with pytest.raises(pb.PbteError) as ei:
+        hc.solve(1)
+    assert ei.value.status == -4
+    s.close()
+    hc.close()
+
+
+def test_cyclic_dependency_is_reported_as_stall():
+    """Three elements whose normals make a directed cycle for direction (1,0): reference throws 'ordering stalled'."""
+    ne, F = 3, 2
+    nbr = np.array([[1, 2], [2, 0], [0, 1]], dtype=np.int32)
+    nrm = np.zeros((ne, F, 3))
+    nrm[:, 0, 0] = 1.0   # face 0: outflow towards the next element
+    nrm[:, 1, 0] = -1.0  # face 1: inflow from the previous element
+    P = pb.ProblemArrays(2, ne, 0, F, 1, 0, 6.28, 1.0, face_nbr=nbr, face_normal=nrm, dir=np.array([[1.0, 0.0, 0.0]]), dir_w=np.array([1.0]))
+    with pytest.raises(RuntimeError):
+        orc.sweep_orders(P)
+    s = pb.Solver(P)
+    with pytest.raises(pb.PbteError) as ei:
+        s.build_schedule()
+    assert ei.value.status == -3
+    s.close()
+
+
+def test_call_order_violations():
+    hc = host_case("c1_tri_p1")
+    s = pb.Solver(hc.problem)
+    with pytest.raises(pb.PbteError) as ei:
+        s.sweep()
+    assert ei.value.status == -8
+    with pytest.raises(pb.PbteError):
+        s.order(0)
+    s.build_schedule()
+    with pytest.raises(pb.PbteError) as ei:
+        s.order(hc.problem.ndir)
+    assert ei.value.status == -1
+    s.close()
+    hc.close()
+
+
+def test_graph_replay_equals_plain_launches_and_is_reproducible():
+    hc = host_case("quad_p2")
+    a = gpu_solve(hc.problem, 3, use_graph=1)
+    b = gpu_solve(hc.problem, 3, use_graph=0)
+    c = gpu_solve(hc.problem, 3, use_graph=1)
+    assert np.array_equal(a["coeff"], b["coeff"]) and np.array_equal(a["Tc"], b["Tc"])
+    assert np.array_equal(a["coeff"], c["coeff"]) and np.array_equal(a["Qc"], c["Qc"])  # bit-reproducible
+    hc.close()
