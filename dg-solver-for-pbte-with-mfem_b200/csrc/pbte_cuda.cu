@@ -335,8 +335,6 @@ int alloc_moment_state(pbte_handle *h)
     CK(cudaMemsetAsync(h->tv_prev.p, 0, h->ne * sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->tc_prev.p, 0, block * sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->error_flag.p, 0, sizeof(int32_t), h->stream));
-    CK(cudaMallocHost(&h->h_norms, 4 * sizeof(double)));
-    CK(cudaMallocHost(&h->h_flag, sizeof(int32_t)));
     return PBTE_OK;
 }
 }  // namespace
@@ -405,6 +403,8 @@ int pbte_cuda_create(const pbte_problem_t *p, const pbte_options_t *opt_in, pbte
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
     CK(cudaEventCreate(&h->ev2));
+    CK(cudaMallocHost(&h->h_norms, 4 * sizeof(double)));
+    CK(cudaMallocHost(&h->h_flag, sizeof(int32_t)));
     h->cache_policy = opt.cache_policy;
     h->kernel_choice = opt.kernel;
     h->use_graph = opt.use_graph;
