@@ -37,10 +37,28 @@ SAMPLE = dict(WORKLOAD, refine=1)  # CPU legs: same workload one refinement leve
 
 
 def flops_per_update(n, dim, faces):
-    """Algorithmic FP64 flops per update: LU + assembly + source/coupling products + triangular solves, per dof."""
+    """Per-element LU path: algorithmic FP64 flops per update: LU + assembly + source/coupling products +
+    triangular solves, per dof."""
     f_in = f_out = faces / 2.0
     per_solve = (2.0 / 3.0) * n ** 3 + 2.0 * (1 + dim + f_out) * n * n + (4 + 2 * f_in) * n * n
     return per_solve / n
+
+
+def flops_per_update_shared(n, mean_inflow_faces):
+    """Shared-operator path (restated algebra): u_e = P x_e + sum_{interior inflow f} Q_f u_nbr(f) + wall vectors:
+    (1 + F_in) dense n x n products per element, F_in = measured mean number of interior inflow faces, plus forming x_e."""
+    return 2.0 * n * (1.0 + mean_inflow_faces) + 2.0
+
+
+def mean_interior_inflow_faces(P, k0, k1):
+    """Mean over (owned direction, element) of the number of interior faces with n.Omega < 0 (exact count for this workload)."""
+    nrm = P.face_normal[:, :, : P.dim]
+    interior = P.face_nbr >= 0
+    tot = 0
+    for k in range(k0, k1):
+        a = nrm @ P.dir[k, : P.dim]
+        tot += int(np.count_nonzero((a < 0.0) & interior))
+    return tot / float(max(k1 - k0, 1) * P.ne)
 
 
 def load_measured_peaks():
@@ -210,7 +228,7 @@ def run_gpu(args, rank, world, local_rank):
     P = hc.problem
     k0, k1 = pb.partition_directions(P.ndir, world, rank)
     stream = torch.cuda.Stream(device=local_rank)
-    solver = pb.Solver(P, device=local_rank, dir_range=(k0, k1), cache_policy=0, stream=stream.cuda_stream)
+    solver = pb.Solver(P, device=local_rank, dir_range=(k0, k1), cache_policy=0, kernel=args.kernel, stream=stream.cuda_stream)
     nclass, nlev = solver.build_schedule()
     ptr, count = solver.moment_buffer()
     # the moment vector as a torch tensor over the library's device buffer: what NCCL all-reduces in place
@@ -288,6 +306,24 @@ def run_gpu(args, rank, world, local_rank):
 
     # ---- the kept C++ API call, PBTESolver::Solve(coeff, macro), with its full host-state upload/download (N = 1 only) --
     solve_call = None
+    general = None
+    if world == 1 and st1.kernel_used == 3 and not args.no_general:
+        # the per-element LU path (any mesh) timed on the same workload, for the record
+        solver.close()
+        g = pb.Solver(P, device=local_rank, dir_range=(k0, k1), cache_policy=0, kernel=2, stream=stream.cuda_stream)
+        g.build_schedule()
+        with torch.cuda.stream(stream):
+            for _ in range(3):
+                g.sweep(); g.finish_iteration()
+            ms = []
+            for _ in range(min(args.steps, 5)):
+                g.sweep(); g.finish_iteration()
+                ms.append(g.stats().last_sweep_ms)
+        gs = float(np.mean(ms)) * 1e-3
+        gf = flops_per_update(P.ndof, P.dim, P.nfaces)
+        general = {"kernel": "warp-register (one pivoted LU per (element, direction, band); any mesh)", "value": U / gs, "unit": UNIT,
+                   "sweep_ms": gs * 1e3, "flop_per_update": gf, "fp64_tflops": gf * U / gs / 1e12}
+        g.close()
     if world == 1:
         solver.close()
         hs = pb.HostSolver(hc, 0)
@@ -307,29 +343,45 @@ def run_gpu(args, rank, world, local_rank):
 
     peaks, peak_src = load_measured_peaks()
     live = pb.measure_peaks(local_rank)
-    fpu = flops_per_update(P.ndof, P.dim, P.nfaces)
     U_rank = P.ndof * P.ne * (k1 - k0) * P.nband
     sweep_s = float(np.mean(sweep_ms)) * 1e-3
-    achieved_tf = fpu * U_rank / sweep_s / 1e12
     fp64_peak = max(live["fp64_fma_tflops"], live["fp64_mma_tflops"])
+    kernel_names = {1: "generic", 2: "warp-register", 3: "shared-operator marching"}
+    if st1.kernel_used == 3:
+        fin = mean_interior_inflow_faces(P, k0, k1)
+        fpu = flops_per_update_shared(P.ndof, fin)
+        kdesc = (f"sweep_march_kernel<{P.ndof}> (one launch per step: one CTA per (direction, band) slot marching through {nlev} wavefront levels,"
+                 f" {st1.n_operator_classes} operator class(es), tile fill {st1.march_fill:.2f}) + moments_from_flux_kernel; {sweep_s * 1e3:.3f} ms per step"
+                 f" by CUDA events on the sweep stream; algorithmic flops = 2n(1+F_in)+2 = {fpu:.1f} per update with F_in = {fin:.3f} interior inflow"
+                 f" faces per element (shared-operator algebra, DESIGN.md); the per-element LU algebra of the reference would be"
+                 f" {flops_per_update(P.ndof, P.dim, P.nfaces):.0f} flop/update")
+        sched = {"classes": nclass, "wavefront_levels": nlev, "kernel": kernel_names[3], "operator_classes": st1.n_operator_classes,
+                 "tiles": st1.march_tiles, "tile_fill": st1.march_fill, "operator_bytes": st1.operator_bytes, "cuda_graph": True}
+    else:
+        fpu = flops_per_update(P.ndof, P.dim, P.nfaces)
+        kdesc = (f"sweep_{'warp' if st1.kernel_used == 2 else 'generic'}_kernel ({nlev} wavefront launches per step, {sweep_s * 1e3:.3f} ms per step by CUDA events"
+                 f" on the sweep stream); algorithmic {fpu:.0f} flop/update (SURVEY 8d)")
+        sched = {"classes": nclass, "wavefront_levels": nlev, "kernel": kernel_names.get(st1.kernel_used, "?"), "cuda_graph": True,
+                 "pivot_cache": "FullLU policy: pivot lanes cached, LU recomputed in registers"}
+    achieved_tf = fpu * U_rank / sweep_s / 1e12
     hbm_gbs = 16.0 * U_rank / sweep_s / 1e9
     launches = int(st1.kernel_launches - st0.kernel_launches)
-    prof = os.path.join(ROOT, "profiles", "r01_c2_ncu_summary.json")
+    prof = os.path.join(ROOT, "profiles", "ncu_summary.json")
     traffic = None
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get("dram_bytes_per_sweep")
+            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    flux_mb = P.ndof * P.ne * (k1 - k0) * P.nband * 8 / 1e6
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"C2: builtin unit-cube-hex refine 2 ({P.ne} hexes), DG order 2 (ndof {P.ndof}), 8 Gauss polar x {azim} uniform azimuth = {P.ndir} directions"
                                f" ({k1 - k0} per GPU), gray SMRT = 2 bands, reference-compatible local matrices; {U} updates per step",
                    "parallelism": f"directions partitioned over {world} GPU(s), one FP64 all-reduce of [Tc|Qc] per step" if world > 1 else "single GPU",
-                   "l2_flush": "none needed: flux (226 MB per GPU) + matrix image (0.4 GB) exceed the 126 MB L2 every step",
-                   "schedule": {"classes": nclass, "wavefront_levels": nlev, "kernel": "warp-register" if st1.kernel_used == 2 else "generic",
-                                "cuda_graph": True, "pivot_cache": "FullLU policy: pivot lanes cached, LU recomputed in registers"},
+                   "l2_flush": f"none needed: the flux ({flux_mb:.0f} MB per GPU) is read and rewritten every step and exceeds the 126 MB L2",
+                   "schedule": sched,
                    "residual_after_run": res},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "what": "per step: Tc,Tv uploaded from pinned host memory, sweep+finish through the C ABI, Tc,Qc,Tv,Qv,residual downloaded; flux stays device resident",
@@ -337,12 +389,13 @@ def run_gpu(args, rank, world, local_rank):
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak, "traffic": traffic,
-                     "note": f"dominant kernel = sweep_warp_kernel<27,3> ({nlev} wavefront launches per step, {sweep_s * 1e3:.3f} ms per step by CUDA events on the sweep stream);"
-                             f" algorithmic {fpu:.0f} flop/update (SURVEY 8d) x {U_rank} updates; peak = FP64 pipe measured live by pbte_cuda_measure_peaks"
+                     "note": f"dominant kernel = {kdesc} x {U_rank} updates; peak = FP64 pipe measured live by pbte_cuda_measure_peaks"
                              f" (DFMA {live['fp64_fma_tflops']:.1f}, DMMA {live['fp64_mma_tflops']:.1f} TFLOP/s)",
                      "hbm": {"achieved": hbm_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "frac": hbm_gbs / peaks.get("hbm_gbs"),
                              "algorithmic_bytes_per_update": 16, "peak_source": peak_src, "live_copy_gbs": live["hbm_copy_gbs"]}},
     }
+    if general is not None:
+        line["general_path"] = general
     if world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_baseline_leg()
@@ -360,6 +413,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-general", action="store_true", help="skip the side measurement of the per-element LU kernel")
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 warp-register, 3 shared-operator marching")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -370,7 +425,8 @@ def main():
     if world == 1 and args.gpus > 1:
         # convenience: re-launch under torchrun, one process per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
-               "--master-port", "29531", os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+               "--master-port", "29531", os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup),
+               "--kernel", str(args.kernel)]
         sys.exit(subprocess.call(cmd))
     run_gpu(args, rank, world, local_rank)
 

@@ -19,8 +19,10 @@ constexpr int kMaxDim = 3;
 //   stiff      [ne][dim][ms]
 //   fmass/fcoup[ne][F][ms]
 //   fint       [ne][F][ndof]       fnormal [ne][F][3]   ftbc [ne][F]   fnbr int32 [ne][F]   basis [ne][ndof]
-//   flux       [ne][nslots][ndof]  persistent angular flux; slot = (owned direction in schedule-class order) * nband + band,
-//                                  so the slots of one schedule class are contiguous for every element
+//   flux       [nslots][ne][ndof]  persistent angular flux; slot = (owned direction in schedule-class order) * nband + band.
+//                                  One slot = one reference block coeff[k][b][s] (ndof x ne, column-major), so uploads and
+//                                  downloads are plain copies, a marching CTA streams one contiguous block and the moment
+//                                  pass is perfectly coalesced
 //   tc_prev    [ne][ndof]          previous-iteration pseudo-temperature (source of the sweep)
 //   partial    [nclass][1+dim][ne][ndof]   per-class moment partial sums written by the sweep (every entry, every sweep)
 //   mom        [1+dim][ne][ndof]   Tc | Qc_0.. : the vector that is all-reduced across GPUs
@@ -40,7 +42,7 @@ struct DevProblem
     const int32_t *cls_slot_begin;  // [nclass+1]
     const uint8_t *cls_out;         // [nclass][ne] faces with n.Omega > 0 for some direction of the class
     const uint8_t *cls_in;          // [nclass][ne] interior faces with n.Omega < 0 for some direction of the class
-    uint8_t *pivots;                // [ne][nslots][ndof] cached pivot lanes (FullLU policy) or nullptr
+    uint8_t *pivots;                // [nslots][ne][ndof] cached pivot lanes (FullLU policy) or nullptr
     int32_t *error_flag;            // device int: first PBTE_ERR_* raised by a kernel
 };
 

@@ -6,7 +6,9 @@
 #include "moments.cuh"
 #include "peaks.cuh"
 #include "schedule.cuh"
+#include "shared_plan.hpp"
 #include "sweep_generic.cuh"
+#include "sweep_shared.cuh"
 #include "sweep_warp.cuh"
 
 #include <algorithm>
@@ -98,6 +100,20 @@ struct pbte_handle
     WarpKernelShape shape{0, 0};
     int kernel_used = 0;
     bool pivots_recorded = false;
+
+    // shared-operator (marching) path
+    double class_tol = 1e-12;
+    int max_classes = 512;
+    pbte_host::SharedPlan plan;
+    int march_ntiles = 0;
+    double march_fill = 0.0;
+    bool march_stage = false;
+    size_t march_smem = 0;
+    DevBuf<int32_t> m_slot_class, m_cls_level_begin, m_level_tile_begin, m_tile_oclass, m_tile_desc, m_cls_op_off, m_cls_op_cnt, m_oc_rep,
+        m_oc_ksrc, m_oc_gsrc, m_cnbr;
+    DevBuf<uint8_t> m_cls_inmask, m_cface;
+    DevBuf<unsigned long long> m_slot_op_base;
+    DevBuf<double> m_ops, m_oph, m_ctbc;
 
     // state
     DevBuf<double> flux, tc_prev, tv_prev, partial, mom, cell, norms, scratch;
@@ -254,6 +270,62 @@ WarpKernelFn pick_warp_kernel(int n, int dim, int piv)
     return nullptr;
 }
 
+DevMarch make_dev_march(pbte_handle *h)
+{
+    DevMarch S{};
+    S.noclass = h->plan.noclass;
+    S.F = h->F;
+    S.slot_class = h->m_slot_class.p;
+    S.cls_level_begin = h->m_cls_level_begin.p;
+    S.level_tile_begin = h->m_level_tile_begin.p;
+    S.tile_oclass = h->m_tile_oclass.p;
+    S.tile_desc = h->m_tile_desc.p;
+    S.cls_inmask = h->m_cls_inmask.p;
+    S.cls_op_off = h->m_cls_op_off.p;
+    S.cls_op_cnt = h->m_cls_op_cnt.p;
+    S.slot_op_base = h->m_slot_op_base.p;
+    S.ops = h->m_ops.p;
+    S.oph = h->m_oph.p;
+    S.ctbc = h->m_ctbc.p;
+    S.oc_rep = h->m_oc_rep.p;
+    S.oc_ksrc = h->m_oc_ksrc.p;
+    S.oc_gsrc = h->m_oc_gsrc.p;
+    S.cface = h->m_cface.p;
+    S.cnbr = h->m_cnbr.p;
+    return S;
+}
+
+// ---- marching-kernel dispatch --------------------------------------------------------------------
+typedef void (*MarchKernelFn)(DevProblem, DevMarch);
+
+template <int N>
+MarchKernelFn pick_stage(bool stage)
+{
+    return stage ? sweep_march_kernel<N, true> : sweep_march_kernel<N, false>;
+}
+
+MarchKernelFn pick_march_kernel(int n, bool stage)
+{
+    switch (n)
+    {
+        case 3: return pick_stage<3>(stage);
+        case 4: return pick_stage<4>(stage);
+        case 6: return pick_stage<6>(stage);
+        case 8: return pick_stage<8>(stage);
+        case 9: return pick_stage<9>(stage);
+        case 10: return pick_stage<10>(stage);
+        case 15: return pick_stage<15>(stage);
+        case 16: return pick_stage<16>(stage);
+        case 20: return pick_stage<20>(stage);
+        case 25: return pick_stage<25>(stage);
+        case 27: return pick_stage<27>(stage);
+        case 35: return pick_stage<35>(stage);
+        case 36: return pick_stage<36>(stage);
+        case 64: return pick_stage<64>(stage);
+        default: return nullptr;
+    }
+}
+
 int check_handle(pbte_handle *h)
 {
     if (!h) return fail(PBTE_ERR_INVALID, "null handle");
@@ -265,6 +337,17 @@ int enqueue_sweep(pbte_handle *h, int piv, int64_t *launch_count)
 {
     const DevProblem P = make_dev_problem(h);
     int64_t launches = 0;
+    if (h->kernel_used == 3)
+    {
+        // one marching CTA per slot, then one streaming pass for the moments
+        const DevMarch S = make_dev_march(h);
+        pick_march_kernel(h->n, h->march_stage)<<<h->nslots(), kMarchThreads, h->march_smem, h->stream>>>(P, S);
+        const size_t block = (size_t)h->ne * h->n;
+        moments_from_flux_kernel<<<(unsigned)((block + 255) / 256), 256, 0, h->stream>>>(P, h->mom.p);
+        CK(cudaGetLastError());
+        if (launch_count) *launch_count = 2;
+        return PBTE_OK;
+    }
     if (h->kernel_used == 2)
     {
         WarpKernelFn fn = pick_warp_kernel(h->n, h->dim, piv);
@@ -321,6 +404,95 @@ int run_norms(pbte_handle *h, double *diff2, double *tv2, double *tc2)
     return PBTE_OK;
 }
 
+// Tile schedule, operator storage and operator construction of the marching path.  *used = false when the automatic
+// choice declines (tiles too empty to beat the per-element kernels).
+int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vector<uint8_t> &cbin, bool *used)
+{
+    *used = false;
+    const pbte_host::SharedPlan &plan = h->plan;
+    const int nclass = h->nclass, F = h->F, n = h->n, ns = h->nslots(), noc = plan.noclass;
+    const pbte_host::MarchSchedule sched = pbte_host::build_march_schedule(plan, nclass, h->h_level.data(), cin.data(), cbin.data());
+    h->march_ntiles = sched.ntiles;
+    h->march_fill = sched.fill;
+    if (h->kernel_choice == 0 && sched.fill < 0.4) return PBTE_OK;
+
+    // operator block layout per slot: for every operator class P, then Q_j of the class's inflow faces (ascending j)
+    const size_t FR = (size_t)frag_doubles(n);
+    std::vector<int32_t> op_off((size_t)nclass * noc), op_cnt(nclass), slot_class(ns);
+    for (int c = 0; c < nclass; ++c)
+    {
+        int cnt = 0;
+        for (int o = 0; o < noc; ++o)
+        {
+            op_off[(size_t)c * noc + o] = cnt;
+            cnt += 1 + __builtin_popcount(sched.cls_inmask[(size_t)c * noc + o]);
+        }
+        op_cnt[c] = cnt;
+    }
+    std::vector<unsigned long long> slot_base(ns);
+    size_t total = 0;
+    int max_cnt = 0;
+    for (int c = 0; c < nclass; ++c)
+    {
+        max_cnt = std::max(max_cnt, (int)op_cnt[c]);
+        for (int s = h->cls_slot_begin[c]; s < h->cls_slot_begin[c + 1]; ++s)
+        {
+            slot_class[s] = c;
+            slot_base[s] = total;
+            total += (size_t)op_cnt[c] * FR;
+        }
+    }
+    int st;
+    if ((st = upload(h->m_slot_class, slot_class.data(), slot_class.size(), h->stream))) return st;
+    if ((st = upload(h->m_cls_level_begin, sched.cls_level_begin.data(), sched.cls_level_begin.size(), h->stream))) return st;
+    if ((st = upload(h->m_level_tile_begin, sched.level_tile_begin.data(), sched.level_tile_begin.size(), h->stream))) return st;
+    if ((st = upload(h->m_tile_oclass, sched.tile_oclass.data(), sched.tile_oclass.size(), h->stream))) return st;
+    if ((st = upload(h->m_tile_desc, sched.tile_desc.data(), sched.tile_desc.size(), h->stream))) return st;
+    if ((st = upload(h->m_cls_inmask, sched.cls_inmask.data(), sched.cls_inmask.size(), h->stream))) return st;
+    if ((st = upload(h->m_cls_op_off, op_off.data(), op_off.size(), h->stream))) return st;
+    if ((st = upload(h->m_cls_op_cnt, op_cnt.data(), op_cnt.size(), h->stream))) return st;
+    if ((st = upload(h->m_slot_op_base, slot_base.data(), slot_base.size(), h->stream))) return st;
+    if ((st = upload(h->m_oc_rep, plan.oc_rep.data(), plan.oc_rep.size(), h->stream))) return st;
+    if ((st = upload(h->m_oc_ksrc, plan.oc_ksrc.data(), plan.oc_ksrc.size(), h->stream))) return st;
+    if ((st = upload(h->m_oc_gsrc, plan.oc_gsrc.data(), plan.oc_gsrc.size(), h->stream))) return st;
+    if ((st = upload(h->m_cnbr, plan.cnbr.data(), plan.cnbr.size(), h->stream))) return st;
+    if ((st = upload(h->m_cface, plan.cface.data(), plan.cface.size(), h->stream))) return st;
+    if ((st = upload(h->m_ctbc, plan.ctbc.data(), plan.ctbc.size(), h->stream))) return st;
+    CK(h->m_ops.alloc(total));
+    const size_t nh = (size_t)ns * noc * F * n;
+    CK(h->m_oph.alloc(nh));
+    CK(cudaMemsetAsync(h->m_oph.p, 0, nh * sizeof(double), h->stream));
+    CK(cudaStreamSynchronize(h->stream));  // the host vectors above go out of scope
+
+    // operators staged in shared memory when a slot's block fits (two CTAs per SM up to 100 KB each, one beyond)
+    int max_optin = 0;
+    CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    const size_t stage_bytes = (size_t)max_cnt * FR * sizeof(double);
+    h->march_stage = stage_bytes + 1024 <= (size_t)max_optin;
+    h->march_smem = h->march_stage ? stage_bytes : 0;
+    MarchKernelFn fn = pick_march_kernel(n, h->march_stage);
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->march_smem));
+
+    const size_t build_smem = 2 * (size_t)n * n * sizeof(double);
+    if (build_smem > (size_t)max_optin || n > 128) return fail(PBTE_ERR_INVALID, "ndof too large for the operator construction kernel");
+    CK(cudaFuncSetAttribute(build_operators_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_smem));
+    const DevProblem P = make_dev_problem(h);
+    const DevMarch S = make_dev_march(h);
+    build_operators_kernel<<<dim3((unsigned)ns, (unsigned)noc), 128, build_smem, h->stream>>>(P, S);
+    ++h->launches;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->h_flag, h->error_flag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (*h->h_flag != 0)
+    {
+        const int flag = *h->h_flag;
+        CK(cudaMemsetAsync(h->error_flag.p, 0, sizeof(int32_t), h->stream));
+        return fail(flag, "singular local system while building the shared operators");
+    }
+    *used = true;
+    return PBTE_OK;
+}
+
 int alloc_moment_state(pbte_handle *h)
 {
     const size_t block = (size_t)h->ne * h->n, nm = 1 + h->dim;
@@ -365,6 +537,8 @@ void pbte_cuda_default_options(pbte_options_t *opt)
     std::memset(opt, 0, sizeof(*opt));
     opt->device = -1;
     opt->use_graph = 1;
+    opt->class_tol = 1e-12;
+    opt->max_classes = 512;
 }
 
 int pbte_cuda_create(const pbte_problem_t *p, const pbte_options_t *opt_in, pbte_handle_t **out)
@@ -408,6 +582,9 @@ int pbte_cuda_create(const pbte_problem_t *p, const pbte_options_t *opt_in, pbte
     h->cache_policy = opt.cache_policy;
     h->kernel_choice = opt.kernel;
     h->use_graph = opt.use_graph;
+    if (opt.class_tol > 0.0) h->class_tol = opt.class_tol;
+    if (opt.max_classes > 0) h->max_classes = opt.max_classes;
+    if (opt.kernel < 0 || opt.kernel > 3) return fail(PBTE_ERR_INVALID, "unknown kernel choice");
     h->dim = p->dim;
     h->ne = p->ne;
     h->n = p->ndof;
@@ -474,6 +651,8 @@ int pbte_cuda_create(const pbte_problem_t *p, const pbte_options_t *opt_in, pbte
         for (size_t i = 0; i < ne * F; ++i)
             if (p->face_nbr[i] == PBTE_FACE_BOUNDARY && std::isnan(p->face_tbc[i])) h->missing_bc = true;
         h->has_matrices = true;
+        // operator classes for the shared-operator path (host-side, needs the caller's arrays: done here)
+        if (h->kernel_choice == 0 || h->kernel_choice == 3) h->plan = pbte_host::classify_elements(*p, h->class_tol, h->max_classes);
     }
     if (p->basis_integrals && ne > 0 && n > 0)
     {
@@ -542,18 +721,20 @@ int pbte_cuda_build_schedule(pbte_handle_t *h)
                                                                            d_out.p, d_bin.p);
     ++h->launches;
     CK(cudaGetLastError());
-    std::vector<uint8_t> in(nm), outm(nm);
+    std::vector<uint8_t> in(nm), outm(nm), binm(nm);
     CK(cudaMemcpyAsync(in.data(), d_in.p, nm, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(outm.data(), d_out.p, nm, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(binm.data(), d_bin.p, nm, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
 
-    // 2. directions with identical upwind sets share one DAG -> one schedule class
+    // 2. directions with identical upwind sets (interior and wall inflow faces) share one DAG -> one schedule class
     std::map<std::string, int> seen;
     h->class_of_dir.assign(nloc, -1);
     std::vector<int> rep;  // representative direction of each class
     for (int k = 0; k < nloc; ++k)
     {
         std::string key(reinterpret_cast<const char *>(in.data() + (size_t)k * ne), ne);
+        key.append(reinterpret_cast<const char *>(binm.data() + (size_t)k * ne), ne);
         auto it = seen.find(key);
         if (it == seen.end())
         {
@@ -576,8 +757,12 @@ int pbte_cuda_build_schedule(pbte_handle_t *h)
             h->slotdir_of_dir[k] = h->cls_slot_begin[c] / std::max(h->nband, 1) + fill[c]++;
         }
     }
-    std::vector<uint8_t> cin((size_t)nclass * ne), cout((size_t)nclass * ne, 0);
-    for (int c = 0; c < nclass; ++c) std::memcpy(cin.data() + (size_t)c * ne, in.data() + (size_t)rep[c] * ne, ne);
+    std::vector<uint8_t> cin((size_t)nclass * ne), cbin((size_t)nclass * ne), cout((size_t)nclass * ne, 0);
+    for (int c = 0; c < nclass; ++c)
+    {
+        std::memcpy(cin.data() + (size_t)c * ne, in.data() + (size_t)rep[c] * ne, ne);
+        std::memcpy(cbin.data() + (size_t)c * ne, binm.data() + (size_t)rep[c] * ne, ne);
+    }
     for (int k = 0; k < nloc; ++k)
     {
         uint8_t *dst = cout.data() + (size_t)h->class_of_dir[k] * ne;
@@ -701,6 +886,17 @@ int pbte_cuda_build_schedule(pbte_handle_t *h)
             const size_t smem = sweep_generic_smem(h->n, h->F);
             CK(cudaFuncSetAttribute(sweep_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
+        // shared-operator marching path: forced (kernel 3) or chosen when the tiles are reasonably full
+        if (h->kernel_choice == 3 && !h->plan.ok)
+            return fail(PBTE_ERR_INVALID, "shared-operator kernel not available: " + (h->plan.why.empty() ? std::string("no plan") : h->plan.why));
+        if (h->kernel_choice == 3 && pick_march_kernel(h->n, false) == nullptr)
+            return fail(PBTE_ERR_INVALID, "shared-operator kernel not instantiated for this ndof");
+        if ((h->kernel_choice == 0 || h->kernel_choice == 3) && h->plan.ok && pick_march_kernel(h->n, false) != nullptr)
+        {
+            bool used = false;
+            if ((st = setup_march(h, cin, cbin, &used))) return st;
+            if (used) h->kernel_used = 3;
+        }
         h->pivots.release();
         h->pivots_recorded = false;
         if (h->kernel_used == 2 && h->cache_policy == 0) CK(h->pivots.alloc((size_t)ne * ns * h->n));
@@ -783,9 +979,9 @@ int pbte_cuda_upload_coeff(pbte_handle_t *h, int32_t k, int32_t band, const doub
     if ((st = coeff_slot(h, k, band, &slot))) return st;
     if (!host) return fail(PBTE_ERR_INVALID, "null host pointer");
     DeviceGuard guard(h->device);
-    const size_t n = h->n;
-    CK(cudaMemcpy2DAsync(h->flux.p + (size_t)slot * n, (size_t)h->nslots() * n * sizeof(double), host, n * sizeof(double), n * sizeof(double),
-                         h->ne, cudaMemcpyHostToDevice, h->stream));
+    // a slot of the flux is exactly one reference block coeff[k][b][s] (ndof x ne, column-major)
+    const size_t block = (size_t)h->ne * h->n;
+    CK(cudaMemcpyAsync(h->flux.p + (size_t)slot * block, host, block * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return PBTE_OK;
 }
@@ -798,9 +994,8 @@ int pbte_cuda_download_coeff(pbte_handle_t *h, int32_t k, int32_t band, double *
     if ((st = coeff_slot(h, k, band, &slot))) return st;
     if (!host) return fail(PBTE_ERR_INVALID, "null host pointer");
     DeviceGuard guard(h->device);
-    const size_t n = h->n;
-    CK(cudaMemcpy2DAsync(host, n * sizeof(double), h->flux.p + (size_t)slot * n, (size_t)h->nslots() * n * sizeof(double), n * sizeof(double),
-                         h->ne, cudaMemcpyDeviceToHost, h->stream));
+    const size_t block = (size_t)h->ne * h->n;
+    CK(cudaMemcpyAsync(host, h->flux.p + (size_t)slot * block, block * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return PBTE_OK;
 }
@@ -1052,6 +1247,10 @@ int pbte_cuda_get_stats(pbte_handle_t *h, pbte_stats_t *s)
     s->kernel_used = h->kernel_used;
     s->n_classes = h->nclass;
     s->max_levels = h->max_levels;
+    s->n_operator_classes = h->plan.ok ? h->plan.noclass : 0;
+    s->march_tiles = h->march_ntiles;
+    s->march_fill = h->march_fill;
+    s->operator_bytes = (int64_t)((h->m_ops.count + h->m_oph.count) * sizeof(double));
     return PBTE_OK;
 }
 

@@ -1,0 +1,350 @@
+// Host-side planning of the shared-operator sweep (operator de-duplication).
+//
+// 1. classify_elements: finds the distinct local matrices of the problem image (entry-wise comparison, relative
+//    tolerance on the max norm) and groups the elements into OPERATOR CLASSES: elements of one class have the same
+//    M, G_d and, face by face in a canonical face order (sorted by normal / face-mass id, so the grouping does not
+//    depend on the per-element face numbering of ElementIntegralData), the same F_f, n_f, K_f and g_f.  For every
+//    (operator class, direction, band) the local system matrix A is therefore the same, and the sweep update
+//        u_e = A^-1 [ M^T (c1 T_old + c2 u_old) - sum_in c_f K_f u_nbr(f) - sum_in,bdr c_f (C/omega) T_bc g_f ]
+//    becomes u_e = P x_e + sum_f Q_f u_nbr(f) + sum_f T_bc(f) h_f with operators shared by the whole class.
+//    Uniformly refined meshes have a handful of classes (1 for Cartesian quads/hexes, tens for refined simplices).
+// 2. build_march_schedule: per upwind-DAG class, the wavefront levels cut into tiles of <= 8 elements of one operator
+//    class (one DMMA m8n8k4 row block), with the upwind neighbour of every (element, canonical face) resolved.
+//
+// Nothing here assumes structure; when the mesh has too many classes `ok` stays false and the per-element kernels run.
+// Header-only and CUDA-free so that tests/native/plan_check.cpp can exercise it on the CPU.
+#pragma once
+
+#include "pbte_cuda.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace pbte_host
+{
+constexpr int kTileElems = 8;     // elements per tile = M of the m8n8k4 MMA
+constexpr int kSrcSkip = -1;      // tile source code: face contributes nothing (outflow / padding)
+constexpr int kSrcWall = -2;      // tile source code: isothermal wall on an inflow face
+
+// Dictionary of distinct vectors of fixed length under |a - b|_max <= tol * |b|_max.
+struct MatDict
+{
+    size_t len = 0;
+    double tol = 1e-12;
+    size_t max_reps = 256;
+    std::vector<const double *> reps;
+    std::vector<double> norm, sum;
+
+    MatDict(size_t len_, double tol_, size_t max_reps_) : len(len_), tol(tol_), max_reps(max_reps_) {}
+
+    // id of the representative equal to m within tol (added when new); -1 when the dictionary is full
+    int find_or_add(const double *m)
+    {
+        double nrm = 0.0, sm = 0.0;
+        for (size_t i = 0; i < len; ++i)
+        {
+            nrm = std::max(nrm, std::fabs(m[i]));
+            sm += m[i];
+        }
+        for (size_t r = 0; r < reps.size(); ++r)
+        {
+            const double bound = tol * norm[r];
+            if (std::fabs(nrm - norm[r]) > bound) continue;
+            if (std::fabs(sm - sum[r]) > bound * (double)len) continue;
+            const double *q = reps[r];
+            bool same = true;
+            for (size_t i = 0; i < len; ++i)
+                if (std::fabs(m[i] - q[i]) > bound)
+                {
+                    same = false;
+                    break;
+                }
+            if (same) return (int)r;
+        }
+        if (reps.size() >= max_reps) return -1;
+        reps.push_back(m);
+        norm.push_back(nrm);
+        sum.push_back(sm);
+        return (int)reps.size() - 1;
+    }
+};
+
+struct SharedPlan
+{
+    bool ok = false;
+    std::string why;  // reason when !ok
+    int ne = 0, n = 0, F = 0, dim = 0;
+    int noclass = 0;  // operator classes
+    int naclass = 0;  // classes of the system matrix alone (diagnostic)
+    std::vector<int32_t> elem_oclass;  // [ne]
+    std::vector<int32_t> cnbr;         // [ne][F] canonical face j -> neighbour element, PBTE_FACE_BOUNDARY or PBTE_FACE_NONE
+    std::vector<uint8_t> cface;        // [ne][F] canonical face j -> local face slot
+    std::vector<double> ctbc;          // [ne][F] wall temperature of canonical face j (0 unless boundary)
+    std::vector<int32_t> oc_rep;       // [noclass] representative element (source of M, G_d, F_f, n_f)
+    std::vector<int32_t> oc_nface;     // [noclass] canonical faces present
+    std::vector<int32_t> oc_ksrc;      // [noclass][F] element*F + local face holding K of canonical face j, or -1
+    std::vector<int32_t> oc_gsrc;      // [noclass][F] element*F + local face holding g of canonical face j, or -1
+};
+
+inline SharedPlan classify_elements(const pbte_problem_t &p, double tol = 1e-12, int max_classes = 512)
+{
+    SharedPlan out;
+    const int ne = out.ne = p.ne, n = out.n = p.ndof, F = out.F = p.nfaces, dim = out.dim = p.dim;
+    const size_t nn = (size_t)n * n;
+    if (ne == 0 || n == 0 || F == 0)
+    {
+        out.why = "empty problem";
+        return out;
+    }
+    const size_t max_reps = (size_t)max_classes;
+    MatDict dM(nn, tol, max_reps), dG(nn, tol, 4 * max_reps), dF(nn, tol, max_reps), dK(nn, tol, max_reps), dg((size_t)n, tol, max_reps),
+        dn(3, tol, 4 * max_reps);
+    struct FaceKey
+    {
+        int nid, fid, f;
+        bool operator<(const FaceKey &o) const { return nid != o.nid ? nid < o.nid : (fid != o.fid ? fid < o.fid : f < o.f); }
+    };
+    std::map<std::vector<int>, int> aclasses;
+    std::vector<int32_t> elem_aclass(ne);
+    std::vector<int32_t> kid((size_t)ne * F, -1), gid((size_t)ne * F, -1);  // per canonical face
+    out.cnbr.assign((size_t)ne * F, PBTE_FACE_NONE);
+    out.cface.assign((size_t)ne * F, 0);
+    out.ctbc.assign((size_t)ne * F, 0.0);
+    std::vector<int> asig;
+    std::vector<FaceKey> faces;
+    for (int e = 0; e < ne; ++e)
+    {
+        asig.clear();
+        int id = dM.find_or_add(p.mass + e * nn);
+        if (id < 0)
+        {
+            out.why = "too many distinct mass matrices";
+            return out;
+        }
+        asig.push_back(id);
+        for (int d = 0; d < dim; ++d)
+        {
+            id = dG.find_or_add(p.stiff + ((size_t)e * dim + d) * nn);
+            if (id < 0)
+            {
+                out.why = "too many distinct stiffness matrices";
+                return out;
+            }
+            asig.push_back(id);
+        }
+        faces.clear();
+        for (int f = 0; f < F; ++f)
+        {
+            const size_t slot = (size_t)e * F + f;
+            if (p.face_nbr[slot] == PBTE_FACE_NONE) continue;
+            const int fid = dF.find_or_add(p.face_mass + slot * nn);
+            const int nid = dn.find_or_add(p.face_normal + slot * 3);
+            if (fid < 0 || nid < 0)
+            {
+                out.why = "too many distinct face matrices or normals";
+                return out;
+            }
+            faces.push_back({nid, fid, f});
+        }
+        std::sort(faces.begin(), faces.end());
+        for (size_t j = 0; j < faces.size(); ++j)
+        {
+            if (j > 0 && faces[j].nid == faces[j - 1].nid && faces[j].fid == faces[j - 1].fid)
+            {
+                out.why = "two faces of one element share normal and face matrix";
+                return out;
+            }
+            const int f = faces[j].f;
+            const size_t slot = (size_t)e * F + f, cs = (size_t)e * F + j;
+            asig.push_back(faces[j].nid);
+            asig.push_back(faces[j].fid);
+            out.cface[cs] = (uint8_t)f;
+            out.cnbr[cs] = p.face_nbr[slot];
+            if (p.face_nbr[slot] >= 0)
+            {
+                kid[cs] = dK.find_or_add(p.face_coupling + slot * nn);
+                if (kid[cs] < 0)
+                {
+                    out.why = "too many distinct coupling matrices";
+                    return out;
+                }
+            }
+            else
+            {
+                out.ctbc[cs] = p.face_tbc[slot];
+                gid[cs] = dg.find_or_add(p.face_integral + slot * n);
+                if (gid[cs] < 0)
+                {
+                    out.why = "too many distinct face integrals";
+                    return out;
+                }
+            }
+        }
+        auto it = aclasses.find(asig);
+        if (it == aclasses.end())
+        {
+            if ((int)aclasses.size() >= max_classes)
+            {
+                out.why = "too many element classes";
+                return out;
+            }
+            it = aclasses.emplace(asig, (int)aclasses.size()).first;
+        }
+        elem_aclass[e] = it->second;
+    }
+    const int na = out.naclass = (int)aclasses.size();
+    // can all elements of an A-class share one K and one g per canonical face?
+    std::vector<int32_t> a_kid((size_t)na * F, -1), a_gid((size_t)na * F, -1);
+    std::vector<uint8_t> a_conflict(na, 0);
+    for (int e = 0; e < ne; ++e)
+    {
+        const int a = elem_aclass[e];
+        for (int j = 0; j < F; ++j)
+        {
+            const size_t cs = (size_t)e * F + j, as = (size_t)a * F + j;
+            if (kid[cs] >= 0)
+            {
+                if (a_kid[as] < 0) a_kid[as] = kid[cs];
+                else if (a_kid[as] != kid[cs]) a_conflict[a] = 1;
+            }
+            if (gid[cs] >= 0)
+            {
+                if (a_gid[as] < 0) a_gid[as] = gid[cs];
+                else if (a_gid[as] != gid[cs]) a_conflict[a] = 1;
+            }
+        }
+    }
+    // operator classes: the A-class itself, or (A-class, K ids, g ids) where those differ inside the A-class
+    std::map<std::vector<int>, int> oclasses;
+    out.elem_oclass.resize(ne);
+    std::vector<int> osig;
+    for (int e = 0; e < ne; ++e)
+    {
+        const int a = elem_aclass[e];
+        osig.assign(1, a);
+        if (a_conflict[a])
+            for (int j = 0; j < F; ++j)
+            {
+                osig.push_back(kid[(size_t)e * F + j]);
+                osig.push_back(gid[(size_t)e * F + j]);
+            }
+        auto it = oclasses.find(osig);
+        if (it == oclasses.end())
+        {
+            if ((int)oclasses.size() >= max_classes)
+            {
+                out.why = "too many operator classes";
+                return out;
+            }
+            it = oclasses.emplace(osig, (int)oclasses.size()).first;
+            out.oc_rep.push_back(e);
+            int nf = 0;
+            for (int j = 0; j < F; ++j)
+                if (out.cnbr[(size_t)e * F + j] != PBTE_FACE_NONE) nf = j + 1;
+            out.oc_nface.push_back(nf);
+            out.oc_ksrc.insert(out.oc_ksrc.end(), F, -1);
+            out.oc_gsrc.insert(out.oc_gsrc.end(), F, -1);
+        }
+        const int o = it->second;
+        out.elem_oclass[e] = o;
+        for (int j = 0; j < F; ++j)
+        {
+            const size_t cs = (size_t)e * F + j, os = (size_t)o * F + j;
+            const int32_t src = (int32_t)((size_t)e * F + out.cface[cs]);
+            if (kid[cs] >= 0 && out.oc_ksrc[os] < 0) out.oc_ksrc[os] = src;
+            if (gid[cs] >= 0 && out.oc_gsrc[os] < 0) out.oc_gsrc[os] = src;
+        }
+    }
+    out.noclass = (int)oclasses.size();
+    out.ok = true;
+    return out;
+}
+
+// Per upwind-DAG class: wavefront levels cut into tiles.
+struct MarchSchedule
+{
+    int nclass = 0, F = 0, ntiles = 0, max_levels = 0;
+    std::vector<int32_t> cls_level_begin;  // [nclass+1] into level_tile_begin (class c has cls_level_begin[c+1]-cls_level_begin[c]-1 levels)
+    std::vector<int32_t> level_tile_begin; // per class: nlevels+1 tile offsets (global tile indices)
+    std::vector<int32_t> tile_oclass;      // [ntiles]
+    std::vector<int32_t> tile_desc;        // [ntiles][1+F][8]: row 0 = elements (-1 padding), row 1+j = source of canonical face j
+    std::vector<uint8_t> cls_inmask;       // [nclass][noclass] canonical inflow faces (interior or wall) of the class representative
+    double fill = 0.0;                     // elements / (8 * tiles)
+};
+
+// level [nclass][ne], cin / cbin [nclass][ne]: bit f (LOCAL face) = interior / wall inflow face of the class
+inline MarchSchedule build_march_schedule(const SharedPlan &plan, int nclass, const int32_t *level, const uint8_t *cin, const uint8_t *cbin)
+{
+    MarchSchedule S;
+    const int ne = plan.ne, F = plan.F;
+    S.nclass = nclass;
+    S.F = F;
+    S.cls_level_begin.assign(nclass + 1, 0);
+    S.cls_inmask.assign((size_t)nclass * plan.noclass, 0);
+    std::vector<std::pair<int64_t, int32_t>> keyed(ne);
+    const int rows = 1 + F;
+    for (int c = 0; c < nclass; ++c)
+    {
+        const int32_t *lv = level + (size_t)c * ne;
+        const uint8_t *mi = cin + (size_t)c * ne, *mb = cbin + (size_t)c * ne;
+        int nlev = 0;
+        for (int e = 0; e < ne; ++e)
+        {
+            nlev = std::max(nlev, lv[e] + 1);
+            keyed[e] = {(int64_t)lv[e] * plan.noclass + plan.elem_oclass[e], e};
+        }
+        std::sort(keyed.begin(), keyed.end());
+        S.max_levels = std::max(S.max_levels, nlev);
+        S.cls_level_begin[c + 1] = S.cls_level_begin[c] + nlev + 1;
+        S.level_tile_begin.resize(S.cls_level_begin[c + 1]);
+        int32_t *ltb = S.level_tile_begin.data() + S.cls_level_begin[c];
+        int cur_level = -1;
+        for (int i = 0; i < ne;)
+        {
+            const int e0 = keyed[i].second, L = lv[e0], o = plan.elem_oclass[e0];
+            while (cur_level < L) ltb[++cur_level] = S.ntiles;
+            int cnt = 0;
+            const size_t base = S.tile_desc.size();
+            S.tile_desc.resize(base + (size_t)rows * kTileElems, kSrcSkip);
+            S.tile_oclass.push_back(o);
+            while (i < ne && cnt < kTileElems && keyed[i].first == (int64_t)L * plan.noclass + o)
+            {
+                const int e = keyed[i].second;
+                S.tile_desc[base + cnt] = e;
+                for (int j = 0; j < F; ++j)
+                {
+                    const size_t cs = (size_t)e * F + j;
+                    const int f = plan.cface[cs];
+                    int32_t code = kSrcSkip;
+                    if (plan.cnbr[cs] >= 0 && (mi[e] >> f & 1u)) code = plan.cnbr[cs];
+                    else if (plan.cnbr[cs] == PBTE_FACE_BOUNDARY && (mb[e] >> f & 1u)) code = kSrcWall;
+                    S.tile_desc[base + (size_t)(1 + j) * kTileElems + cnt] = code;
+                }
+                ++cnt;
+                ++i;
+            }
+            ++S.ntiles;
+        }
+        while (cur_level < nlev) ltb[++cur_level] = S.ntiles;
+        for (int o = 0; o < plan.noclass; ++o)
+        {
+            const int e = plan.oc_rep[o];
+            unsigned m = 0;
+            for (int j = 0; j < F; ++j)
+            {
+                const size_t cs = (size_t)e * F + j;
+                if (plan.cnbr[cs] == PBTE_FACE_NONE) continue;
+                const int f = plan.cface[cs];
+                if (((mi[e] | mb[e]) >> f) & 1u) m |= 1u << j;
+            }
+            S.cls_inmask[(size_t)c * plan.noclass + o] = (uint8_t)m;
+        }
+    }
+    S.fill = S.ntiles ? (double)nclass * ne / ((double)kTileElems * S.ntiles) : 0.0;
+    return S;
+}
+}  // namespace pbte_host

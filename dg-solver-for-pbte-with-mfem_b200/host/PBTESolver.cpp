@@ -1,5 +1,7 @@
 #include "PBTESolver.hpp"
 
+#include <cstdlib>
+
 #include "CudaCheck.hpp"
 #include "ProblemImage.hpp"
 
@@ -28,6 +30,9 @@ PBTESolver::PBTESolver(const mfem::Mesh &mesh, const mfem::FiniteElementSpace &f
     pbte_options_t opt;
     pbte_cuda_default_options(&opt);
     opt.cache_policy = policy == CachePolicy::FullLU ? 0 : 1;
+    // GPU knobs stay out of config.yaml (the reference's parsers must keep working): environment variables
+    if (const char *k = std::getenv("PBTE_KERNEL")) opt.kernel = std::atoi(k);          // 0 auto, 1 generic, 2 warp, 3 shared-operator
+    if (const char *t = std::getenv("PBTE_CLASS_TOL")) opt.class_tol = std::atof(t);
     ThrowOnStatus(pbte_cuda_create(&image.View(), &opt, &dev_), "pbte_cuda_create");
     ThrowOnStatus(pbte_cuda_build_schedule(dev_), "pbte_cuda_build_schedule");
 }

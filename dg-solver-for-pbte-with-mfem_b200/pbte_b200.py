@@ -42,13 +42,16 @@ class Problem(C.Structure):
 
 class Options(C.Structure):
     _fields_ = [("device", C.c_int32), ("dir_begin", C.c_int32), ("dir_end", C.c_int32), ("cache_policy", C.c_int32),
-                ("kernel", C.c_int32), ("use_graph", C.c_int32), ("stream", C.c_void_p), ("reserved", C.c_int32 * 8)]
+                ("kernel", C.c_int32), ("use_graph", C.c_int32), ("stream", C.c_void_p), ("class_tol", C.c_double),
+                ("max_classes", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("sweeps", C.c_int64), ("last_sweep_ms", C.c_double),
                 ("last_finish_ms", C.c_double), ("flux_bytes", C.c_int64), ("launches_per_sweep", C.c_int64),
-                ("kernel_used", C.c_int32), ("n_classes", C.c_int32), ("max_levels", C.c_int32), ("reserved", C.c_int32)]
+                ("kernel_used", C.c_int32), ("n_classes", C.c_int32), ("max_levels", C.c_int32),
+                ("n_operator_classes", C.c_int32), ("march_tiles", C.c_int32), ("reserved", C.c_int32),
+                ("march_fill", C.c_double), ("operator_bytes", C.c_int64)]
 
 
 class HostSpec(C.Structure):

@@ -99,10 +99,15 @@ typedef struct pbte_options
     int32_t dir_begin;  /* this handle sweeps directions [dir_begin, dir_end); 0,0 = all             */
     int32_t dir_end;    /*   (the (angle,band) partition of SURVEY §8e: one handle per GPU)          */
     int32_t cache_policy; /* 0 = FullLU (cache pivot sequences, CachePolicy::FullLU), 1 = OnTheFly    */
-    int32_t kernel;     /* 0 = auto, 1 = generic shared-memory kernel, 2 = warp-register kernel      */
+    int32_t kernel;     /* 0 = auto, 1 = generic shared-memory kernel, 2 = warp-register kernel (both: one pivoted LU per
+                           (element, direction, band), any mesh), 3 = shared-operator marching kernel (elements grouped
+                           into operator classes, FP64 tensor-core MMAs; PBTE_ERR_INVALID when the mesh has too many classes) */
     int32_t use_graph;  /* 1 = replay the per-iteration launch sequence as a CUDA graph (default), 0 = plain launches */
     void *stream;       /* cudaStream_t to run on; NULL = a stream owned by the handle               */
-    int32_t reserved[8];
+    double class_tol;   /* relative max-norm tolerance under which two local matrices count as equal when elements are
+                           grouped into operator classes; <= 0 = default 1e-12                      */
+    int32_t max_classes; /* give up on the shared-operator path beyond this many classes; <= 0 = default 512 */
+    int32_t reserved[5];
 } pbte_options_t;
 
 typedef struct pbte_handle pbte_handle_t;
@@ -172,10 +177,14 @@ typedef struct pbte_stats
     double last_finish_ms;    /* device time of the last finish_iteration                              */
     int64_t flux_bytes;       /* bytes of persistent angular flux held by this handle                  */
     int64_t launches_per_sweep;
-    int32_t kernel_used;      /* 1 generic, 2 warp-register                                            */
-    int32_t n_classes;
+    int32_t kernel_used;      /* 1 generic, 2 warp-register, 3 shared-operator marching                */
+    int32_t n_classes;        /* distinct upwind DAGs among the owned directions                       */
     int32_t max_levels;
+    int32_t n_operator_classes; /* element classes with identical local operators (0 = not classified)  */
+    int32_t march_tiles;      /* 8-element tiles of the marching schedule (all DAG classes)            */
     int32_t reserved;
+    double march_fill;        /* elements / (8 * tiles): occupancy of the MMA row blocks               */
+    int64_t operator_bytes;   /* device bytes of the precomputed shared operators                      */
 } pbte_stats_t;
 int pbte_cuda_get_stats(pbte_handle_t *h, pbte_stats_t *stats);
 /* The cudaStream_t the handle launches on (for CUDA-event timing by the caller). */

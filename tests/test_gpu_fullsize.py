@@ -36,11 +36,12 @@ def test_c2_orders_are_topological_and_sorted_by_pass(c2):
     s.close()
 
 
-def test_c2_linearity_and_partition_invariance(c2):
+@pytest.mark.parametrize("kernel", [2, 3])
+def test_c2_linearity_and_partition_invariance(c2, kernel):
     """From a cold start the iterate is linear in the wall temperatures: doubling them doubles every number exactly
     (power-of-two scaling commutes with FP64 rounding); two direction halves sum to the full moments."""
     P = c2.problem
-    s = pb.Solver(P)
+    s = pb.Solver(P, kernel=kernel)
     s.build_schedule()
     _, _, h1 = s.solve(3, 0.0)
     m1 = s.download_moments()
@@ -48,7 +49,7 @@ def test_c2_linearity_and_partition_invariance(c2):
     s.close()
     P2 = pb.ProblemArrays(P.dim, P.ne, P.ndof, P.nfaces, P.ndir, P.nband, P.omega, P.heat_cap_v,
                           **{f: getattr(P, f) for f in pb.ProblemArrays.FIELDS if f != "face_tbc"}, face_tbc=2.0 * P.face_tbc)
-    s = pb.Solver(P2)
+    s = pb.Solver(P2, kernel=kernel)
     s.build_schedule()
     _, _, h2 = s.solve(3, 0.0)
     m2 = s.download_moments()
@@ -57,14 +58,14 @@ def test_c2_linearity_and_partition_invariance(c2):
     assert np.array_equal(h1, h2)
     s.close()
     # one sweep split over two direction blocks
-    full = pb.Solver(P)
+    full = pb.Solver(P, kernel=kernel)
     full.build_schedule()
     full.sweep()
     want = full.download_moments()
     full.close()
     tc = np.zeros_like(want["Tc"])
     for r in range(2):
-        sv = pb.Solver(P, dir_range=pb.partition_directions(P.ndir, 2, r))
+        sv = pb.Solver(P, kernel=kernel, dir_range=pb.partition_directions(P.ndir, 2, r))
         sv.build_schedule()
         sv.sweep()
         tc += sv.download_moments()["Tc"]
@@ -72,13 +73,15 @@ def test_c2_linearity_and_partition_invariance(c2):
     assert np.abs(tc - want["Tc"]).max() <= 1e-13 * np.abs(want["Tc"]).max()
 
 
-def test_c2_local_systems_are_solved_to_backward_stability(c2):
+@pytest.mark.parametrize("kernel", [2, 3])
+def test_c2_local_systems_are_solved_to_backward_stability(c2, kernel):
     """Spot check of A u = r on sampled (direction, band, element) systems after one sweep, assembled independently here."""
     P = c2.problem
     n, F, dim = P.ndof, P.nfaces, P.dim
-    s = pb.Solver(P)
+    s = pb.Solver(P, kernel=kernel)
     s.build_schedule()
     s.sweep()
+    assert s.stats().kernel_used == kernel
     nu_max = P.inv_kn.max()
     rng = np.random.default_rng(3)
     for _ in range(12):
