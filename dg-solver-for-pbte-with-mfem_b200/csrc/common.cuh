@@ -19,17 +19,18 @@ constexpr int kMaxDim = 3;
 //   stiff      [ne][dim][ms]
 //   fmass/fcoup[ne][F][ms]
 //   fint       [ne][F][ndof]       fnormal [ne][F][3]   ftbc [ne][F]   fnbr int32 [ne][F]   basis [ne][ndof]
-//   flux       [nslots][ne][ndof]  persistent angular flux; slot = (owned direction in schedule-class order) * nband + band.
+//   flux       [nslots][ne][np]    persistent angular flux; slot = (owned direction in schedule-class order) * nband + band.
 //                                  One slot = one reference block coeff[k][b][s] (ndof x ne, column-major), so uploads and
 //                                  downloads are plain copies, a marching CTA streams one contiguous block and the moment
 //                                  pass is perfectly coalesced
-//   tc_prev    [ne][ndof]          previous-iteration pseudo-temperature (source of the sweep)
+//   tc_prev    [ne][np]            previous-iteration pseudo-temperature (source of the sweep); np = ndof rounded up to even so
+//                                  that every row is 16-byte aligned (asynchronous 16-byte copies); the padding stays zero
 //   partial    [nclass][1+dim][ne][ndof]   per-class moment partial sums written by the sweep (every entry, every sweep)
 //   mom        [1+dim][ne][ndof]   Tc | Qc_0.. : the vector that is all-reduced across GPUs
 //   slot_*     per-slot scalars: direction (3), v, c1 = nu*C/omega, c2 = nu_max - nu, cb = C/omega, moment factors
 struct DevProblem
 {
-    int dim, ne, n, F, nband, nslots, ms, nclass;
+    int dim, ne, n, np, F, nband, nslots, ms, nclass;  // np = row stride (doubles) of flux and tc_prev: n rounded up to even
     double nu_max;
     const double *mass, *massT, *stiff, *fmass, *fcoup, *fint, *fnormal, *ftbc, *basis;
     const int32_t *fnbr;

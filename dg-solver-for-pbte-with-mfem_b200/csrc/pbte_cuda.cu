@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -71,7 +72,7 @@ struct pbte_handle
     int cache_policy = 0, kernel_choice = 0, use_graph = 1;
 
     // sizes
-    int dim = 0, ne = 0, n = 0, F = 0, ndir = 0, nband = 0, ms = 0;
+    int dim = 0, ne = 0, n = 0, np = 0, F = 0, ndir = 0, nband = 0, ms = 0;  // np: padded row stride of flux / tc_prev
     int k0 = 0, k1 = 0;  // owned directions [k0, k1)
     int nloc() const { return k1 - k0; }
     int nslots() const { return nloc() * nband; }
@@ -108,6 +109,9 @@ struct pbte_handle
     int march_ntiles = 0;
     double march_fill = 0.0;
     bool march_stage = false;
+    int march_h_smem = 0;
+    int march_ring = 0, march_nv = 0;  // tile-ring slots per CTA, staged vectors per slot
+    int mom_chunks = 1;  // slot chunks of the moment pass
     size_t march_smem = 0;
     DevBuf<int32_t> m_slot_class, m_cls_level_begin, m_level_tile_begin, m_tile_oclass, m_tile_desc, m_cls_op_off, m_cls_op_cnt, m_oc_rep,
         m_oc_ksrc, m_oc_gsrc, m_cnbr;
@@ -116,7 +120,7 @@ struct pbte_handle
     DevBuf<double> m_ops, m_oph, m_ctbc;
 
     // state
-    DevBuf<double> flux, tc_prev, tv_prev, partial, mom, cell, norms, scratch;
+    DevBuf<double> flux, tc_prev, tv_prev, partial, mom, cell, norms, scratch, block_part;
     DevBuf<int32_t> error_flag;
     double *h_norms = nullptr;  // pinned [4]
     int32_t *h_flag = nullptr;  // pinned
@@ -190,6 +194,7 @@ DevProblem make_dev_problem(pbte_handle *h)
     P.dim = h->dim;
     P.ne = h->ne;
     P.n = h->n;
+    P.np = h->np;
     P.F = h->F;
     P.nband = h->nband;
     P.nslots = h->nslots();
@@ -274,6 +279,9 @@ DevMarch make_dev_march(pbte_handle *h)
 {
     DevMarch S{};
     S.noclass = h->plan.noclass;
+    S.h_smem = h->march_h_smem;
+    S.ring = h->march_ring;
+    S.nv = h->march_nv;
     S.F = h->F;
     S.slot_class = h->m_slot_class.p;
     S.cls_level_begin = h->m_cls_level_begin.p;
@@ -342,10 +350,12 @@ int enqueue_sweep(pbte_handle *h, int piv, int64_t *launch_count)
         // one marching CTA per slot, then one streaming pass for the moments
         const DevMarch S = make_dev_march(h);
         pick_march_kernel(h->n, h->march_stage)<<<h->nslots(), kMarchThreads, h->march_smem, h->stream>>>(P, S);
-        const size_t block = (size_t)h->ne * h->n;
-        moments_from_flux_kernel<<<(unsigned)((block + 255) / 256), 256, 0, h->stream>>>(P, h->mom.p);
+        const size_t block = (size_t)h->ne * h->n, count = (size_t)(1 + h->dim) * block;
+        const int chunks = h->mom_chunks, per = (h->nslots() + chunks - 1) / chunks;
+        moments_from_flux_kernel<<<dim3((unsigned)((block + 255) / 256), (unsigned)chunks), 256, 0, h->stream>>>(P, chunks > 1 ? h->partial.p : h->mom.p, per);
+        if (chunks > 1) reduce_partials_kernel<<<(unsigned)((count + 255) / 256), 256, 0, h->stream>>>(count, chunks, h->partial.p, h->mom.p);
         CK(cudaGetLastError());
-        if (launch_count) *launch_count = 2;
+        if (launch_count) *launch_count = chunks > 1 ? 3 : 2;
         return PBTE_OK;
     }
     if (h->kernel_used == 2)
@@ -468,8 +478,31 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
     int max_optin = 0;
     CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     const size_t stage_bytes = (size_t)max_cnt * FR * sizeof(double);
-    h->march_stage = stage_bytes + 1024 <= (size_t)max_optin;
-    h->march_smem = h->march_stage ? stage_bytes : 0;
+    // shared memory of a marching CTA: operators (staged when they fit) + metadata/barriers + tile ring.  Two CTAs per SM when
+    // that leaves room for a ring of >= 6 tiles each, one CTA otherwise; without room for operators they are read through L1.
+    h->march_nv = 2 + sched.max_inflow;
+    const size_t h_all = (size_t)noc * F * n;
+    h->march_h_smem = h_all * sizeof(double) <= 16 * 1024;
+    const size_t h_doubles = h->march_h_smem ? h_all : 0;
+    const size_t slot_bytes = march_slot_bytes(n, sched.rows, h->march_nv);
+    const size_t sm_total = (size_t)max_optin, sm_half = (228 * 1024) / 2 - 2048;
+    auto ring_for = [&](size_t budget, bool stage, int *ring) {
+        const size_t fixed = (stage ? stage_bytes : 0) + 64;
+        for (int r = 16; r >= 4; --r)
+            if (fixed + march_meta_bytes(sched.max_levels, noc, r, h_doubles) + (size_t)r * slot_bytes <= budget)
+            {
+                *ring = r;
+                return true;
+            }
+        return false;
+    };
+    int ring = 0;
+    if (ring_for(sm_half, true, &ring) && ring >= 6) h->march_stage = true;
+    else if (ring_for(sm_total - 1024, true, &ring)) h->march_stage = true;
+    else if (ring_for(sm_half, false, &ring) || ring_for(sm_total - 1024, false, &ring)) h->march_stage = false;
+    else return fail(PBTE_ERR_INVALID, "marching kernel does not fit in shared memory for this ndof / level count");
+    h->march_ring = ring;
+    h->march_smem = (h->march_stage ? stage_bytes : 0) + 64 + march_meta_bytes(sched.max_levels, noc, ring, h_doubles) + (size_t)ring * slot_bytes;
     MarchKernelFn fn = pick_march_kernel(n, h->march_stage);
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->march_smem));
 
@@ -489,6 +522,14 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
         CK(cudaMemsetAsync(h->error_flag.p, 0, sizeof(int32_t), h->stream));
         return fail(flag, "singular local system while building the shared operators");
     }
+    // moment pass: enough slot chunks that ~400k threads stream the flux (8 loads in flight each)
+    {
+        const size_t block = (size_t)h->ne * n;
+        int chunks = (int)std::min<size_t>((400000 + block - 1) / block, (size_t)std::max(1, ns / 16));
+        chunks = std::max(1, std::min(chunks, 64));
+        h->mom_chunks = chunks;
+        if ((size_t)chunks > (size_t)nclass) CK(h->partial.alloc((size_t)chunks * (1 + h->dim) * block));
+    }
     *used = true;
     return PBTE_OK;
 }
@@ -499,13 +540,13 @@ int alloc_moment_state(pbte_handle *h)
     CK(h->mom.alloc(nm * block));
     CK(h->cell.alloc(nm * h->ne));
     CK(h->tv_prev.alloc(h->ne));
-    CK(h->tc_prev.alloc(block));
+    CK(h->tc_prev.alloc((size_t)h->ne * h->np));
     CK(h->norms.alloc(4));
     CK(h->error_flag.alloc(1));
     CK(cudaMemsetAsync(h->mom.p, 0, nm * block * sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->cell.p, 0, nm * h->ne * sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->tv_prev.p, 0, h->ne * sizeof(double), h->stream));
-    CK(cudaMemsetAsync(h->tc_prev.p, 0, block * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->tc_prev.p, 0, h->tc_prev.count * sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->error_flag.p, 0, sizeof(int32_t), h->stream));
     return PBTE_OK;
 }
@@ -588,6 +629,7 @@ int pbte_cuda_create(const pbte_problem_t *p, const pbte_options_t *opt_in, pbte
     h->dim = p->dim;
     h->ne = p->ne;
     h->n = p->ndof;
+    h->np = (p->ndof + 1) & ~1;
     h->F = p->nfaces;
     h->ndir = p->ndir;
     h->nband = p->nband;
@@ -667,7 +709,7 @@ int pbte_cuda_create(const pbte_problem_t *p, const pbte_options_t *opt_in, pbte
     }
     if (h->has_matrices && h->has_bands && h->has_dirs)
     {
-        const size_t fl = ne * (size_t)h->nslots() * n;
+        const size_t fl = ne * (size_t)h->nslots() * h->np;
         CK(h->flux.alloc(fl));
         CK(cudaMemsetAsync(h->flux.p, 0, fl * sizeof(double), h->stream));
     }
@@ -899,7 +941,7 @@ int pbte_cuda_build_schedule(pbte_handle_t *h)
         }
         h->pivots.release();
         h->pivots_recorded = false;
-        if (h->kernel_used == 2 && h->cache_policy == 0) CK(h->pivots.alloc((size_t)ne * ns * h->n));
+        if (h->kernel_used == 2 && h->cache_policy == 0) CK(h->pivots.alloc((size_t)ne * ns * h->np));
     }
     h->scheduled = true;
     return PBTE_OK;
@@ -980,8 +1022,9 @@ int pbte_cuda_upload_coeff(pbte_handle_t *h, int32_t k, int32_t band, const doub
     if (!host) return fail(PBTE_ERR_INVALID, "null host pointer");
     DeviceGuard guard(h->device);
     // a slot of the flux is exactly one reference block coeff[k][b][s] (ndof x ne, column-major)
-    const size_t block = (size_t)h->ne * h->n;
-    CK(cudaMemcpyAsync(h->flux.p + (size_t)slot * block, host, block * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    const size_t n = h->n, np = h->np;
+    CK(cudaMemcpy2DAsync(h->flux.p + (size_t)slot * h->ne * np, np * sizeof(double), host, n * sizeof(double), n * sizeof(double), h->ne,
+                         cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return PBTE_OK;
 }
@@ -994,8 +1037,9 @@ int pbte_cuda_download_coeff(pbte_handle_t *h, int32_t k, int32_t band, double *
     if ((st = coeff_slot(h, k, band, &slot))) return st;
     if (!host) return fail(PBTE_ERR_INVALID, "null host pointer");
     DeviceGuard guard(h->device);
-    const size_t block = (size_t)h->ne * h->n;
-    CK(cudaMemcpyAsync(host, h->flux.p + (size_t)slot * block, block * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    const size_t n = h->n, np = h->np;
+    CK(cudaMemcpy2DAsync(host, n * sizeof(double), h->flux.p + (size_t)slot * h->ne * np, np * sizeof(double), n * sizeof(double), h->ne,
+                         cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return PBTE_OK;
 }
@@ -1009,7 +1053,8 @@ int pbte_cuda_upload_moments(pbte_handle_t *h, const double *Tc, const double *T
     const size_t block = (size_t)h->ne * h->n;
     if (Tc)
     {
-        CK(cudaMemcpyAsync(h->tc_prev.p, Tc, block * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpy2DAsync(h->tc_prev.p, h->np * sizeof(double), Tc, h->n * sizeof(double), h->n * sizeof(double), h->ne, cudaMemcpyHostToDevice,
+                             h->stream));
         CK(cudaMemcpyAsync(h->mom.p, Tc, block * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     }
     if (Tv)
@@ -1104,14 +1149,27 @@ int pbte_cuda_finish_iteration(pbte_handle_t *h, double *residual)
     if (st) return st;
     if (!h->mom.p || !h->has_basis) return fail(PBTE_ERR_STATE, "finish_iteration needs basis_integrals in the problem image");
     DeviceGuard guard(h->device);
-    if ((st = run_finalize(h))) return st;
+    // cell integrals, norms of the stop test and the hand-over Tv_prev <- Tv, Tc_prev <- Tc (src/PBTESolver.cpp:313-329) in two launches
     double d2 = 0, t2 = 0, c2 = 0;
-    if ((st = run_norms(h, &d2, &t2, &c2))) return st;
-    // Tv_prev <- Tv, Tc_prev <- Tc   (src/PBTESolver.cpp:328-329)
-    CK(cudaMemcpyAsync(h->tv_prev.p, h->cell.p, h->ne * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->tc_prev.p, h->mom.p, (size_t)h->ne * h->n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    {
+        int seg = 1;
+        while (seg < h->n && seg < 32) seg <<= 1;
+        const size_t threads = (size_t)(1 + h->dim) * h->ne * seg;
+        const unsigned nblocks = (unsigned)((threads + 255) / 256);
+        if (h->block_part.count < (size_t)nblocks * 3) CK(h->block_part.alloc((size_t)nblocks * 3));
+        finish_cells_kernel<<<nblocks, 256, 0, h->stream>>>(h->ne, h->n, h->np, 1 + h->dim, seg, h->mom.p, h->basis.p, h->cell.p, h->tv_prev.p,
+                                                           h->tc_prev.p, h->block_part.p);
+        finish_norms_kernel<<<1, 256, 0, h->stream>>>((int)nblocks, h->block_part.p, h->norms.p);
+        h->launches += 2;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h->h_norms, h->norms.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->h_flag, h->error_flag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    }
     CK(cudaEventRecord(h->ev2, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    d2 = h->h_norms[0];
+    t2 = h->h_norms[1];
+    c2 = h->h_norms[2];
     if (h->sweep_timed)
     {
         float ms = 0.f;

@@ -267,11 +267,12 @@ inline SharedPlan classify_elements(const pbte_problem_t &p, double tol = 1e-12,
 // Per upwind-DAG class: wavefront levels cut into tiles.
 struct MarchSchedule
 {
-    int nclass = 0, F = 0, ntiles = 0, max_levels = 0;
+    int nclass = 0, F = 0, rows = 0, ntiles = 0, max_levels = 0, max_inflow = 0;  // rows = 2 + F descriptor rows of 8 ints per tile
     std::vector<int32_t> cls_level_begin;  // [nclass+1] into level_tile_begin (class c has cls_level_begin[c+1]-cls_level_begin[c]-1 levels)
     std::vector<int32_t> level_tile_begin; // per class: nlevels+1 tile offsets (global tile indices)
     std::vector<int32_t> tile_oclass;      // [ntiles]
-    std::vector<int32_t> tile_desc;        // [ntiles][1+F][8]: row 0 = elements (-1 padding), row 1+j = source of canonical face j
+    std::vector<int32_t> tile_desc;        // [ntiles][2+F][8]: row 0 = elements (-1 padding), row 1+m = source of the m-th inflow face of the
+                                           // tile's class, row 1+F = header {operator class, level, tile index in class, 0...}
     std::vector<uint8_t> cls_inmask;       // [nclass][noclass] canonical inflow faces (interior or wall) of the class representative
     double fill = 0.0;                     // elements / (8 * tiles)
 };
@@ -286,11 +287,27 @@ inline MarchSchedule build_march_schedule(const SharedPlan &plan, int nclass, co
     S.cls_level_begin.assign(nclass + 1, 0);
     S.cls_inmask.assign((size_t)nclass * plan.noclass, 0);
     std::vector<std::pair<int64_t, int32_t>> keyed(ne);
-    const int rows = 1 + F;
+    const int rows = S.rows = 2 + F;
     for (int c = 0; c < nclass; ++c)
     {
         const int32_t *lv = level + (size_t)c * ne;
         const uint8_t *mi = cin + (size_t)c * ne, *mb = cbin + (size_t)c * ne;
+        // canonical inflow faces (interior or wall) of every operator class, from its representative's exact masks
+        uint8_t *inm = S.cls_inmask.data() + (size_t)c * plan.noclass;
+        for (int o = 0; o < plan.noclass; ++o)
+        {
+            const int e = plan.oc_rep[o];
+            unsigned m = 0;
+            for (int j = 0; j < F; ++j)
+            {
+                const size_t cs = (size_t)e * F + j;
+                if (plan.cnbr[cs] == PBTE_FACE_NONE) continue;
+                const int f = plan.cface[cs];
+                if (((mi[e] | mb[e]) >> f) & 1u) m |= 1u << j;
+            }
+            inm[o] = (uint8_t)m;
+            S.max_inflow = std::max(S.max_inflow, (int)__builtin_popcount(m));
+        }
         int nlev = 0;
         for (int e = 0; e < ne; ++e)
         {
@@ -311,18 +328,29 @@ inline MarchSchedule build_march_schedule(const SharedPlan &plan, int nclass, co
             const size_t base = S.tile_desc.size();
             S.tile_desc.resize(base + (size_t)rows * kTileElems, kSrcSkip);
             S.tile_oclass.push_back(o);
+            {
+                int32_t *hdr = S.tile_desc.data() + base + (size_t)(1 + F) * kTileElems;
+                for (int k = 0; k < kTileElems; ++k) hdr[k] = 0;
+                hdr[0] = o;
+                hdr[1] = L;
+                hdr[2] = S.ntiles - ltb[0];
+            }
             while (i < ne && cnt < kTileElems && keyed[i].first == (int64_t)L * plan.noclass + o)
             {
                 const int e = keyed[i].second;
                 S.tile_desc[base + cnt] = e;
-                for (int j = 0; j < F; ++j)
+                // row 1+m = m-th inflow face of the operator class (ascending canonical face index): the kernel reads the
+                // rows without knowing the class
+                int m = 0;
+                for (unsigned rest = inm[o]; rest; rest &= rest - 1, ++m)
                 {
+                    const int j = __builtin_ctz(rest);
                     const size_t cs = (size_t)e * F + j;
                     const int f = plan.cface[cs];
                     int32_t code = kSrcSkip;
                     if (plan.cnbr[cs] >= 0 && (mi[e] >> f & 1u)) code = plan.cnbr[cs];
                     else if (plan.cnbr[cs] == PBTE_FACE_BOUNDARY && (mb[e] >> f & 1u)) code = kSrcWall;
-                    S.tile_desc[base + (size_t)(1 + j) * kTileElems + cnt] = code;
+                    S.tile_desc[base + (size_t)(1 + m) * kTileElems + cnt] = code;
                 }
                 ++cnt;
                 ++i;
@@ -330,19 +358,6 @@ inline MarchSchedule build_march_schedule(const SharedPlan &plan, int nclass, co
             ++S.ntiles;
         }
         while (cur_level < nlev) ltb[++cur_level] = S.ntiles;
-        for (int o = 0; o < plan.noclass; ++o)
-        {
-            const int e = plan.oc_rep[o];
-            unsigned m = 0;
-            for (int j = 0; j < F; ++j)
-            {
-                const size_t cs = (size_t)e * F + j;
-                if (plan.cnbr[cs] == PBTE_FACE_NONE) continue;
-                const int f = plan.cface[cs];
-                if (((mi[e] | mb[e]) >> f) & 1u) m |= 1u << j;
-            }
-            S.cls_inmask[(size_t)c * plan.noclass + o] = (uint8_t)m;
-        }
     }
     S.fill = S.ntiles ? (double)nclass * ne / ((double)kTileElems * S.ntiles) : 0.0;
     return S;

@@ -56,12 +56,12 @@ __global__ void __launch_bounds__(128) sweep_generic_kernel(DevProblem P, const 
         }
         // source vector c1*T_old + c2*u_old and the upwind neighbour fluxes
         for (int i = t; i < n; i += T)
-            vec[i] = c1 * P.tc_prev[(size_t)e * n + i] + c2 * P.flux[((size_t)s * P.ne + e) * n + i];
+            vec[i] = c1 * P.tc_prev[(size_t)e * P.np + i] + c2 * P.flux[((size_t)s * P.ne + e) * P.np + i];
         for (int f = 0; f < F; ++f)
         {
             const int nb = nbr[f];
             if (nb >= 0)
-                for (int i = t; i < n; i += T) vec[(size_t)(1 + f) * n + i] = P.flux[((size_t)s * P.ne + nb) * n + i];
+                for (int i = t; i < n; i += T) vec[(size_t)(1 + f) * n + i] = P.flux[((size_t)s * P.ne + nb) * P.np + i];
         }
         __syncthreads();
         // A = nu_max*M - v*sum_d Omega_d G_d + sum_{outflow f} v*a_f F_f
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(128) sweep_generic_kernel(DevProblem P, const 
         for (int i = t; i < n; i += T)
         {
             const double x = b[i];
-            P.flux[((size_t)s * P.ne + e) * n + i] = x;
+            P.flux[((size_t)s * P.ne + e) * P.np + i] = x;
             if (i == t)  // thread i owns dof i when n <= blockDim; larger n handled below
             {
                 accT += P.slot_mf[s] * x;

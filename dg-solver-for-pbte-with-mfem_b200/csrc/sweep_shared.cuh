@@ -20,12 +20,14 @@
 namespace pbte_dev
 {
 constexpr int kTile = 8;             // elements per tile (must equal pbte_host::kTileElems)
-constexpr int kMarchThreads = 256;   // 8 warps per marching CTA
+constexpr int kSrcSkipCode = -1;     // pbte_host::kSrcSkip
 constexpr int kSrcWallCode = -2;     // pbte_host::kSrcWall
 
 struct DevMarch
 {
     int noclass, F;
+    int h_smem;    // 1: the slot's wall vectors h_f are staged in shared memory (they fit), 0: read through L1
+    int ring, nv;  // tile-ring slots per CTA; staged vectors per slot = 2 (u_old, T_old) + max inflow faces of any class
     const int32_t *slot_class;        // [nslots] upwind-DAG class of the slot
     const int32_t *cls_level_begin;   // [nclass+1] into level_tile_begin
     const int32_t *level_tile_begin;  // per class nlevels+1 tile offsets
@@ -280,110 +282,345 @@ __device__ __forceinline__ void bulk_stage(void *dst, const void *src, uint32_t 
     }
 }
 
-// grid = nslots CTAs of kMarchThreads threads; dynamic shared memory = the slot's operator block when STAGE
+// ---------------------------------------------------------------------------------------------------------------
+// mbarrier / asynchronous-copy primitives of the marching kernel
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok = 0;
+    while (!ok)
+    {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+// 16-byte asynchronous copy global -> shared through L2 (src_bytes = 0 writes zeros)
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, uint32_t src_bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+// the barrier receives one arrival from this thread once all its earlier cp.async have landed
+__device__ __forceinline__ void cp_async_arrive(uint64_t *bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int kMaxIn = 4;          // inflow faces whose wall temperature a consumer lane prefetches (tri 2, quad/hex dim, tet 3)
+constexpr int kConsumerWarps = 4;  // one MMA warp per SM sub-partition
+constexpr int kSrcWarps = 2;       // source loaders (run ahead of the wavefront); warp p takes tiles p, p + kSrcWarps, ...
+constexpr int kNbrWarps = 2;       // upwind-neighbour loaders (follow the wavefront), same interleaving
+constexpr int kMarchThreads = (kConsumerWarps + kSrcWarps + kNbrWarps) * 32;
+
+// shared-memory row stride (doubles) of a staged element vector: 4*KS rounded so that the four element rows a half warp reads
+// with one LDS.64 fall into disjoint bank groups (stride mod 16 in {4, 12})
+__host__ __device__ constexpr int stage_stride(int n)
+{
+    const int ns = ((n + 3) / 4) * 4;
+    return (ns % 16 == 0 || ns % 16 == 8) ? ns + 4 : ns;
+}
+// bytes of one ring slot: tile descriptor (rows x 8 int32) + nv staged vectors of 8 elements
+__host__ __device__ inline size_t march_slot_bytes(int n, int rows, int nv) { return (size_t)rows * 32 + (size_t)nv * kTile * stage_stride(n) * sizeof(double); }
+// bytes of metadata and barriers: level offsets, inflow masks, operator offsets; full/empty per ring slot, one barrier per level;
+// h_doubles wall-vector entries staged when they fit
+__host__ __device__ inline size_t march_meta_bytes(int max_levels, int noclass, int ring, size_t h_doubles)
+{
+    size_t ints = (size_t)max_levels + 1 + 2 * (size_t)noclass;
+    ints = (ints + 3) & ~(size_t)3;
+    return ints * sizeof(int32_t) + sizeof(uint64_t) * (2 * (size_t)ring + (size_t)max_levels) + sizeof(double) * h_doubles;
+}
+
+// grid = nslots CTAs of kMarchThreads threads.  Dynamic shared memory = [operators (STAGE) | metadata | barriers | tile ring].
+//
+// Warp-specialised pipeline over the slot's tile sequence i = 0 .. NT-1 (level-major, so round-robin assignment keeps the
+// consumers balanced inside every level); ring slot = i mod R:
+//   source producer   waits empty[slot]; cp.async of the tile descriptor and of the u_old / T_old rows of its 8 elements.
+//                     Independent of the current sweep: runs up to R tiles ahead and hides the HBM latency.
+//   neighbour producer waits empty[slot] and the barrier of the previous level (all its tiles stored); cp.async of the upwind
+//                     neighbour rows (L2 hits: written by this CTA a level ago).  Both producers complete full[slot].
+//   consumer w        tiles i = w mod 4: waits full[slot]; U = X P^T + sum_m Unbr_m Q_m^T by mma.sync m8n8k4 FP64 with A
+//                     fragments from the ring and B fragments from the staged operators; releases empty[slot]; adds wall
+//                     terms, stores the tile, arrives on the barrier of its level.
 template <int N, bool STAGE>
 __global__ void __launch_bounds__(kMarchThreads, 2) sweep_march_kernel(DevProblem P, DevMarch S)
 {
     using G = Frag<N>;
     constexpr int MT = G::MT, KS = G::KS, FR = G::FR;
+    constexpr int NP = (N + 1) & ~1;        // global row stride (doubles): 16-byte aligned rows
+    constexpr int NS = stage_stride(N);     // shared-memory row stride
+    constexpr int CH = NP / 2;              // 16-byte chunks per row
     extern __shared__ __align__(128) unsigned char sm_raw[];
     __shared__ __align__(8) uint64_t s_bar;
     const int s = blockIdx.x;
     const int c = S.slot_class[s];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int F = S.F, rows = 1 + F;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int F = S.F, rows = 2 + F, noc = S.noclass, R = S.ring, nv = S.nv;
     const double *ops = S.ops + S.slot_op_base[s];
+    const int lb = S.cls_level_begin[c], nlev = S.cls_level_begin[c + 1] - lb - 1;
+    const size_t op_bytes = STAGE ? (size_t)S.cls_op_cnt[c] * (FR * sizeof(double)) : 0;
+
+    // ---- shared memory carve-up ---------------------------------------------------------------------------------
+    int32_t *ltb = reinterpret_cast<int32_t *>(sm_raw + op_bytes);  // [nlev+1] tile offsets of the levels
+    int32_t *s_inm = ltb + nlev + 1;                                 // [noclass] inflow masks
+    int32_t *s_opoff = s_inm + noc;                                  // [noclass] operator offsets (units of FR)
+    const size_t meta_ints = ((size_t)nlev + 1 + 2 * (size_t)noc + 3) & ~(size_t)3;
+    uint64_t *full = reinterpret_cast<uint64_t *>(sm_raw + op_bytes + meta_ints * sizeof(int32_t));  // [R]
+    uint64_t *empty = full + R;                                                                     // [R]
+    uint64_t *level_bar = empty + R;                                                                // [nlev]
+    const size_t slot_bytes = (size_t)rows * 32 + (size_t)nv * kTile * NS * sizeof(double);
+    double *s_h = reinterpret_cast<double *>(level_bar + nlev);  // [noclass][F][N] wall vectors of this slot (when S.h_smem)
+    const size_t h_doubles = S.h_smem ? (size_t)noc * F * N : 0;
+    unsigned char *ring = reinterpret_cast<unsigned char *>(s_h + h_doubles);
+    ring = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(ring) + 15) & ~(uintptr_t)15);
+    for (size_t i = threadIdx.x; i < h_doubles; i += blockDim.x) s_h[i] = S.oph[(size_t)s * noc * F * N + i];
+
+    for (int i = threadIdx.x; i <= nlev; i += blockDim.x) ltb[i] = S.level_tile_begin[lb + i];
+    for (int i = threadIdx.x; i < noc; i += blockDim.x)
+    {
+        s_inm[i] = S.cls_inmask[(size_t)c * noc + i];
+        s_opoff[i] = S.cls_op_off[(size_t)c * noc + i];
+    }
+    // the ring starts zeroed: copies write NP doubles per row, the k padding up to NS stays zero for the whole kernel
+    for (size_t i = threadIdx.x; i < (size_t)R * slot_bytes / 16; i += blockDim.x) reinterpret_cast<uint4 *>(ring)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * R + nlev; i += blockDim.x)
+    {
+        uint32_t count;
+        if (i < R) count = 2 * 32;                                        // full: one source and one neighbour warp, every lane
+        else if (i < 2 * R) count = 1;                                    // empty: lane 0 of the consuming warp
+        else count = (uint32_t)(ltb[i - 2 * R + 1] - ltb[i - 2 * R]);       // level: lane 0 of the warp of every tile of the level
+        mbar_init(full + i, count);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (STAGE)
     {
-        bulk_stage(sm_raw, ops, (uint32_t)S.cls_op_cnt[c] * (uint32_t)(FR * sizeof(double)), &s_bar);
+        bulk_stage(sm_raw, ops, (uint32_t)op_bytes, &s_bar);  // contains a CTA barrier
         ops = reinterpret_cast<const double *>(sm_raw);
     }
-    const int lb = S.cls_level_begin[c], nlev = S.cls_level_begin[c + 1] - lb - 1;
-    const int32_t *ltb = S.level_tile_begin + lb;
-    const uint8_t *inmask = S.cls_inmask + (size_t)c * S.noclass;
-    const int32_t *opoff = S.cls_op_off + (size_t)c * S.noclass;
-    const double c1 = P.slot_c1[s], c2 = P.slot_c2[s];
-    double *u = P.flux + (size_t)s * P.ne * N;
-    const double *oph = S.oph + (size_t)s * S.noclass * F * N;
-    const int q = lane >> 2, r = lane & 3;
+    __syncthreads();
 
-    for (int L = 0; L < nlev; ++L)
+    const int tbase = ltb[0], NT = ltb[nlev] - tbase;
+    double *u = P.flux + (size_t)s * P.ne * NP;
+
+    // Copy patterns of the producers.  A tile needs 16 source rows (u_old and T_old of its 8 elements) and 8 rows per inflow
+    // face, NP doubles each.  The 16-byte chunks are dealt to the lanes in memory order (chunk k*32 + lane), so one cp.async
+    // instruction covers whole contiguous rows: full 32-byte sectors and few distinct cache lines per instruction (a row per
+    // lane would be bound by the one-line-per-cycle tag stage of L1TEX: 16 B/clk/SM measured, tools/copy_probe.cu).  The
+    // (row, chunk) of every (k, lane) is fixed, so it is packed once: bits 0-4 row, bits 5-9 chunk, bits 16-31 byte offset
+    // of the chunk inside the staged vectors.
+    auto pack_pattern = [&](int idx, int nrows) -> int {
+        const int row = idx / CH, ch = idx - row * CH;
+        return idx < nrows * CH ? (row | (ch << 5) | ((row * NS * 8 + ch * 16) << 16)) : -1;
+    };
+    if (warp >= kConsumerWarps && warp < kConsumerWarps + kSrcWarps)
     {
-        const int t1 = ltb[L + 1];
-        for (int t = ltb[L] + warp; t < t1; t += nwarps)
+        // ---- source producer ------------------------------------------------------------------------------------
+        constexpr int IT = (16 * CH + 31) / 32;
+        int pat[IT];
+        const unsigned char *pbase[IT];  // base pointer (u or T_old) + chunk offset of (k, lane)
+#pragma unroll
+        for (int k = 0; k < IT; ++k)
         {
-            const int32_t *desc = S.tile_desc + (size_t)t * rows * kTile;
-            const int e = __ldg(desc + q);
-            const int o = __ldg(S.tile_oclass + t);
-            const unsigned inm = inmask[o];
-            const double *op = ops + (size_t)opoff[o] * FR;
+            pat[k] = pack_pattern(k * 32 + lane, 16);
+            const int row = pat[k] & 31, ch = (pat[k] >> 5) & 31;
+            pbase[k] = reinterpret_cast<const unsigned char *>(row < 8 ? u : P.tc_prev) + ch * 16;
+        }
+        const int q = lane & 7;  // lanes 0-7 hold the elements of the u_old rows, lanes 8-15 the same elements for the T_old rows
+        const int first = warp - kConsumerWarps;
+        int e_next = first < NT ? __ldg(S.tile_desc + (size_t)(tbase + first) * rows * kTile + q) : -1;
+        for (int i = first; i < NT; i += kSrcWarps)
+        {
+            const int slot = i % R, it = i / R;
+            const int e = e_next;
+            const int32_t *desc_g = S.tile_desc + (size_t)(tbase + i) * rows * kTile;
+            if (i + kSrcWarps < NT) e_next = __ldg(desc_g + (size_t)kSrcWarps * rows * kTile + q);
+            if (it > 0) mbar_wait(empty + slot, (it - 1) & 1);
+            unsigned char *sl = ring + (size_t)slot * slot_bytes;
+            const uint32_t vb = smem_u32(sl + rows * 32);
+#pragma unroll
+            for (int k = 0; k < IT; ++k)
+            {
+                const int er = __shfl_sync(0xffffffffu, e, pat[k] & 15);
+                if (pat[k] >= 0)
+                {
+                    const unsigned char *src = pbase[k] + (size_t)(er < 0 ? 0 : er) * (NP * 8);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vb + ((unsigned)pat[k] >> 16)), "l"(src), "r"(er >= 0 ? 16u : 0u)
+                                 : "memory");
+                }
+            }
+            if (lane < rows * 2) cp_async16(sl + lane * 16, reinterpret_cast<const unsigned char *>(desc_g) + lane * 16, 16u);
+            cp_async_arrive(full + slot);
+        }
+    }
+    else if (warp >= kConsumerWarps + kSrcWarps)
+    {
+        // ---- upwind-neighbour producer --------------------------------------------------------------------------
+        constexpr int IT = CH;  // up to 4 inflow faces (32 rows) per pass: 32*CH chunks
+        int pat[IT];
+#pragma unroll
+        for (int k = 0; k < IT; ++k) pat[k] = pack_pattern(k * 32 + lane, 32);
+        const unsigned char *ub = reinterpret_cast<const unsigned char *>(u);
+        const int q = lane & 7, mq = lane >> 3;
+        int waited = -1;  // levels [0, waited] are known to be complete
+        const int first = warp - kConsumerWarps - kSrcWarps;
+        const int32_t *d0 = S.tile_desc + (size_t)(tbase + first) * rows * kTile;
+        int o_next = first < NT ? __ldg(d0 + (1 + F) * kTile) : 0, L_next = first < NT ? __ldg(d0 + (1 + F) * kTile + 1) : 0;
+        int code_next = first < NT ? __ldg(d0 + (1 + mq) * kTile + q) : -1;  // rows 1..4 always exist (rows = 2 + F, F >= 3)
+        for (int i = first; i < NT; i += kNbrWarps)
+        {
+            const int slot = i % R, it = i / R;
+            const int o = o_next, L = L_next, code0 = code_next;
+            const int32_t *desc_g = S.tile_desc + (size_t)(tbase + i) * rows * kTile;
+            if (i + kNbrWarps < NT)
+            {
+                const int32_t *dn = desc_g + (size_t)kNbrWarps * rows * kTile;
+                o_next = __ldg(dn + (1 + F) * kTile);
+                L_next = __ldg(dn + (1 + F) * kTile + 1);
+                code_next = __ldg(dn + (1 + mq) * kTile + q);
+            }
+            if (it > 0) mbar_wait(empty + slot, (it - 1) & 1);
+            if (L - 1 > waited)
+            {
+                mbar_wait(level_bar + (L - 1), 0);  // every tile of the previous level (hence of all earlier ones) is stored
+                waited = L - 1;
+            }
+            const int nin = __popc((unsigned)s_inm[o]);
+            unsigned char *sl = ring + (size_t)slot * slot_bytes;
+            for (int m0 = 0; m0 < nin; m0 += 4)
+            {
+                // lane (mq, q) holds the source code of row mq*8 + q of this pass
+                const int code = m0 == 0 ? code0 : ((m0 + mq < nin) ? __ldg(desc_g + (1 + m0 + mq) * kTile + q) : kSrcSkipCode);
+                const int nrow = min(nin - m0, 4) * kTile;
+                const uint32_t vb = smem_u32(sl + rows * 32) + (uint32_t)((2 + m0) * kTile * NS * 8);
+#pragma unroll
+                for (int k = 0; k < IT; ++k)
+                {
+                    const int cr = __shfl_sync(0xffffffffu, code, pat[k] & 31);
+                    if (pat[k] >= 0 && (pat[k] & 31) < nrow)
+                    {
+                        const unsigned char *src = ub + (size_t)(cr < 0 ? 0 : cr) * (NP * 8) + ((pat[k] >> 5) & 31) * 16;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vb + ((unsigned)pat[k] >> 16)), "l"(src), "r"(cr >= 0 ? 16u : 0u)
+                                     : "memory");
+                    }
+                }
+            }
+            cp_async_arrive(full + slot);
+        }
+    }
+    else
+    {
+        // ---- consumers ----------------------------------------------------------------------------------------------
+        const int q = lane >> 2, r = lane & 3;
+        const double c1 = P.slot_c1[s], c2 = P.slot_c2[s];
+        const double *oph = S.h_smem ? s_h : S.oph + (size_t)s * noc * F * N;
+        for (int i = warp; i < NT; i += kConsumerWarps)
+        {
+            const int slot = i % R, it = i / R;
+            const unsigned char *sl = ring + (size_t)slot * slot_bytes;
+            const int32_t *sd = reinterpret_cast<const int32_t *>(sl);
+            const double *vec = reinterpret_cast<const double *>(sl + rows * 32) + (size_t)q * NS + r;
+            mbar_wait(full + slot, it & 1);
+            const int e = sd[q], o = sd[(1 + F) * kTile], L = sd[(1 + F) * kTile + 1];
+            const unsigned inm = (unsigned)s_inm[o];
+            const int nin = __popc(inm);
+            const double *op = ops + (size_t)s_opoff[o] * FR;
+            // wall temperatures of this lane's element are fetched now and used after the MMAs (their L2 latency is hidden)
+            unsigned wall = 0;
+            double tb[kMaxIn];
+            {
+                unsigned rest = inm;
+#pragma unroll
+                for (int m = 0; m < kMaxIn; ++m)
+                {
+                    tb[m] = 0.0;
+                    if (rest)
+                    {
+                        if (sd[(1 + m) * kTile + q] == kSrcWallCode)
+                        {
+                            wall |= 1u << m;
+                            tb[m] = __ldg(S.ctbc + (size_t)e * F + (__ffs(rest) - 1));
+                        }
+                        rest &= rest - 1;
+                    }
+                }
+            }
             double acc[MT][2];
 #pragma unroll
             for (int I = 0; I < MT; ++I) acc[I][0] = acc[I][1] = 0.0;
-
             // source / pseudo-time term: X = c1 T_old + c2 u_old
+#pragma unroll
+            for (int kk = 0; kk < KS; ++kk)
             {
-                double x[KS];
-                const double *ue = u + (size_t)(e < 0 ? 0 : e) * N, *te = P.tc_prev + (size_t)(e < 0 ? 0 : e) * N;
+                const double x = fma(c2, vec[4 * kk], c1 * vec[(size_t)kTile * NS + 4 * kk]);
 #pragma unroll
-                for (int kk = 0; kk < KS; ++kk)
+                for (int I = 0; I < MT; ++I)
                 {
-                    const int row = 4 * kk + r;
-                    x[kk] = (e >= 0 && row < N) ? fma(c2, __ldcg(ue + row), c1 * __ldg(te + row)) : 0.0;
+                    const double b = STAGE ? op[(I * KS + kk) * 32 + lane] : __ldg(op + (I * KS + kk) * 32 + lane);
+                    dmma_m8n8k4(acc[I][0], acc[I][1], x, b);
                 }
-#pragma unroll
-                for (int kk = 0; kk < KS; ++kk)
-#pragma unroll
-                    for (int I = 0; I < MT; ++I)
-                    {
-                        const double b = STAGE ? op[(I * KS + kk) * 32 + lane] : __ldg(op + (I * KS + kk) * 32 + lane);
-                        dmma_m8n8k4(acc[I][0], acc[I][1], x[kk], b);
-                    }
             }
             // upwind couplings of the inflow faces
-            int m = 1;
-            unsigned wall = 0;
-            for (unsigned rest = inm; rest; rest &= rest - 1, ++m)
+            for (int m = 0; m < nin; ++m)
             {
-                const int j = __ffs(rest) - 1;
-                const int code = __ldg(desc + (1 + j) * kTile + q);
-                if (code == kSrcWallCode) wall |= 1u << j;
+                const int code = sd[(1 + m) * kTile + q];
+                if (m >= kMaxIn && code == kSrcWallCode) wall |= 1u << m;
                 if (__ballot_sync(0xffffffffu, code >= 0) == 0u) continue;
-                double x[KS];
-                const double *un = u + (size_t)(code < 0 ? 0 : code) * N;
+                const double *vm = vec + (size_t)(2 + m) * kTile * NS;
+                const double *oq = op + (size_t)(1 + m) * FR;
 #pragma unroll
                 for (int kk = 0; kk < KS; ++kk)
                 {
-                    const int row = 4 * kk + r;
-                    x[kk] = (code >= 0 && row < N) ? __ldcg(un + row) : 0.0;
-                }
-                const double *oq = op + (size_t)m * FR;
-#pragma unroll
-                for (int kk = 0; kk < KS; ++kk)
+                    const double x = vm[4 * kk];
 #pragma unroll
                     for (int I = 0; I < MT; ++I)
                     {
                         const double b = STAGE ? oq[(I * KS + kk) * 32 + lane] : __ldg(oq + (I * KS + kk) * 32 + lane);
-                        dmma_m8n8k4(acc[I][0], acc[I][1], x[kk], b);
+                        dmma_m8n8k4(acc[I][0], acc[I][1], x, b);
                     }
-            }
-            // isothermal walls on inflow faces: + T_bc h_j   (this lane owns element q, dofs 8I + 2r + {0,1})
-            for (; wall; wall &= wall - 1)
-            {
-                const int j = __ffs(wall) - 1;
-                const double tb = __ldg(S.ctbc + (size_t)e * F + j);
-                const double *hj = oph + ((size_t)o * F + j) * N;
-#pragma unroll
-                for (int I = 0; I < MT; ++I)
-                {
-                    const int d0 = 8 * I + 2 * r;
-                    if (d0 < N) acc[I][0] = fma(tb, __ldg(hj + d0), acc[I][0]);
-                    if (d0 + 1 < N) acc[I][1] = fma(tb, __ldg(hj + d0 + 1), acc[I][1]);
                 }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + slot);  // every staged value of the tile has been consumed by an MMA
+            // isothermal walls on inflow faces: + T_bc h_j   (this lane owns element q, dofs 8I + 2r + {0,1})
+            if (wall)
+            {
+                auto add_wall = [&](int j, double t) {
+                    const double *hj = oph + ((size_t)o * F + j) * N;
+#pragma unroll
+                    for (int I = 0; I < MT; ++I)
+                    {
+                        const int d0 = 8 * I + 2 * r;
+                        if (d0 < N) acc[I][0] = fma(t, hj[d0], acc[I][0]);
+                        if (d0 + 1 < N) acc[I][1] = fma(t, hj[d0 + 1], acc[I][1]);
+                    }
+                };
+                unsigned rest = inm;
+#pragma unroll
+                for (int m = 0; m < kMaxIn; ++m)
+                    if (rest)
+                    {
+                        if (wall >> m & 1u) add_wall(__ffs(rest) - 1, tb[m]);
+                        rest &= rest - 1;
+                    }
+                for (int m = kMaxIn; rest; ++m, rest &= rest - 1)
+                    if (wall >> m & 1u) add_wall(__ffs(rest) - 1, __ldg(S.ctbc + (size_t)e * F + (__ffs(rest) - 1)));
             }
             if (e >= 0)
             {
-                double *dst = u + (size_t)e * N;
+                double *dst = u + (size_t)e * NP;
 #pragma unroll
                 for (int I = 0; I < MT; ++I)
                 {
@@ -392,26 +629,31 @@ __global__ void __launch_bounds__(kMarchThreads, 2) sweep_march_kernel(DevProble
                     if (d0 + 1 < N) dst[d0 + 1] = acc[I][1];
                 }
             }
+            __syncwarp();  // orders the stores of all lanes before lane 0's release
+            if (lane == 0) mbar_arrive(level_bar + L);
         }
-        __syncthreads();  // level L complete (its stores are visible to the CTA) before level L+1 reads it
     }
 }
 
-// mom[m][x] = sum_s fac_m[s] * flux[s][x], x = (element, dof) flattened; slots in ascending order (fixed summation order)
-__global__ void __launch_bounds__(256) moments_from_flux_kernel(DevProblem P, double *__restrict__ mom)
+// out[y][m][x] = sum_{s in slot chunk y} fac_m[s] * flux[s][x], x = (element, dof) flattened; slots in ascending order.
+// grid (ceil(ne*n / 256), chunks): the slot range is cut into gridDim.y chunks so that enough loads are in flight to fill
+// HBM; the chunk partials are summed in ascending order by reduce_partials_kernel (fixed summation order: bit-reproducible).
+__global__ void __launch_bounds__(256) moments_from_flux_kernel(DevProblem P, double *__restrict__ out, int slots_per_chunk)
 {
     const size_t block = (size_t)P.ne * P.n;
     const size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (x >= block) return;
-    const int dim = P.dim, ns = P.nslots;
+    const int dim = P.dim;
+    const int s_begin = blockIdx.y * slots_per_chunk, s_end = min(P.nslots, s_begin + slots_per_chunk);
     double t = 0.0, q0 = 0.0, q1 = 0.0, q2 = 0.0;
-    const double *u = P.flux + x;
-    int s = 0;
-    for (; s + 8 <= ns; s += 8)
+    const size_t e = x / P.n, sblock = (size_t)P.ne * P.np;  // flux rows are padded to np doubles
+    const double *u = P.flux + e * P.np + (x - e * P.n);
+    int s = s_begin;
+    for (; s + 8 <= s_end; s += 8)
     {
         double v[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = __ldcs(u + (size_t)(s + k) * block);
+        for (int k = 0; k < 8; ++k) v[k] = __ldcs(u + (size_t)(s + k) * sblock);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
         {
@@ -421,14 +663,15 @@ __global__ void __launch_bounds__(256) moments_from_flux_kernel(DevProblem P, do
             q2 = fma(P.slot_qf[3 * (s + k) + 2], v[k], q2);
         }
     }
-    for (; s < ns; ++s)
+    for (; s < s_end; ++s)
     {
-        const double v = __ldcs(u + (size_t)s * block);
+        const double v = __ldcs(u + (size_t)s * sblock);
         t = fma(P.slot_mf[s], v, t);
         q0 = fma(P.slot_qf[3 * s], v, q0);
         q1 = fma(P.slot_qf[3 * s + 1], v, q1);
         q2 = fma(P.slot_qf[3 * s + 2], v, q2);
     }
+    double *mom = out + (size_t)blockIdx.y * (1 + dim) * block;
     mom[x] = t;
     mom[block + x] = q0;
     if (dim > 1) mom[2 * block + x] = q1;

@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sweep_warp_kernel(DevProble
 
     const bool active = lane < N;
     const int row = active ? lane : 0;  // idle lanes shadow row 0 (their results are discarded)
-    const double T_old = P.tc_prev[(size_t)e * N + row];
+    const double T_old = P.tc_prev[(size_t)e * P.np + row];
     double accT = 0.0, accQ[kMaxDim] = {0.0, 0.0, 0.0};
     bool singular = false;
 
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sweep_warp_kernel(DevProble
         {
             const int s = sd + band;
             const double v = P.slot_v[s], c1 = P.slot_c1[s], c2 = P.slot_c2[s], cb = P.slot_cb[s];
-            const size_t uoff = ((size_t)s * P.ne + e) * N;
+            const size_t uoff = ((size_t)s * P.ne + e) * P.np;
 
             // stage the source vector and the upwind neighbour fluxes (lane j holds entry j)
             if (active) vec[lane] = c1 * T_old + c2 * P.flux[uoff + lane];
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sweep_warp_kernel(DevProble
                 if (f < F && af[f] < 0.0)
                 {
                     const int nb = P.fnbr[(size_t)e * F + f];
-                    if (nb >= 0 && active) vec[(1 + f) * N + lane] = P.flux[((size_t)s * P.ne + nb) * N + lane];
+                    if (nb >= 0 && active) vec[(1 + f) * N + lane] = P.flux[((size_t)s * P.ne + nb) * P.np + lane];
                 }
             }
             __syncwarp();

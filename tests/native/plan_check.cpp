@@ -124,7 +124,7 @@ extern "C" int plan_check_run(const pbte_problem_t *p, double tol, int max_class
     // slot tables
     double nu_max = 0.0;
     for (int b = 0; b < nband; ++b) nu_max = std::max(nu_max, p->inv_kn[b]);
-    const int noc = plan.noclass, rows = 1 + F;
+    const int noc = plan.noclass, rows = S.rows;
     std::vector<int> op_off((size_t)nclass * noc), op_cnt(nclass);
     for (int c = 0; c < nclass; ++c)
     {
@@ -219,7 +219,7 @@ extern "C" int plan_check_run(const pbte_problem_t *p, double tol, int max_class
                             for (int j = 0; j < F; ++j)
                             {
                                 if (!(inm >> j & 1u)) continue;
-                                const int code = desc[(1 + j) * kTileElems + qd];
+                                const int code = desc[m * kTileElems + qd];  // row 1 + (m-1): m counts from 1 here
                                 if (code >= 0)
                                 {
                                     const double *q = op + (size_t)m * nn, *un = u + (size_t)code * n;
