@@ -349,7 +349,7 @@ int enqueue_sweep(pbte_handle *h, int piv, int64_t *launch_count)
     {
         // one marching CTA per slot, then one streaming pass for the moments
         const DevMarch S = make_dev_march(h);
-        pick_march_kernel(h->n, h->march_stage)<<<h->nslots(), kMarchThreads, h->march_smem, h->stream>>>(P, S);
+        pick_march_kernel(h->n, h->march_stage)<<<h->nslots(), march_threads(h->n), h->march_smem, h->stream>>>(P, S);
         const size_t block = (size_t)h->ne * h->n, count = (size_t)(1 + h->dim) * block;
         const int chunks = h->mom_chunks, per = (h->nslots() + chunks - 1) / chunks;
         moments_from_flux_kernel<<<dim3((unsigned)((block + 255) / 256), (unsigned)chunks), 256, 0, h->stream>>>(P, chunks > 1 ? h->partial.p : h->mom.p, per);
@@ -467,7 +467,15 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
     if ((st = upload(h->m_oc_gsrc, plan.oc_gsrc.data(), plan.oc_gsrc.size(), h->stream))) return st;
     if ((st = upload(h->m_cnbr, plan.cnbr.data(), plan.cnbr.size(), h->stream))) return st;
     if ((st = upload(h->m_cface, plan.cface.data(), plan.cface.size(), h->stream))) return st;
-    if ((st = upload(h->m_ctbc, plan.ctbc.data(), plan.ctbc.size(), h->stream))) return st;
+    {
+        // wall temperatures with rows padded to an even count (16-byte rows for the asynchronous copies)
+        const int Fp = (F + 1) & ~1;
+        std::vector<double> tb((size_t)h->ne * Fp, 0.0);
+        for (int e = 0; e < h->ne; ++e)
+            for (int j = 0; j < F; ++j) tb[(size_t)e * Fp + j] = plan.ctbc[(size_t)e * F + j];
+        if ((st = upload(h->m_ctbc, tb.data(), tb.size(), h->stream))) return st;
+        CK(cudaStreamSynchronize(h->stream));
+    }
     CK(h->m_ops.alloc(total));
     const size_t nh = (size_t)ns * noc * F * n;
     CK(h->m_oph.alloc(nh));
@@ -484,11 +492,13 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
     const size_t h_all = (size_t)noc * F * n;
     h->march_h_smem = h_all * sizeof(double) <= 16 * 1024;
     const size_t h_doubles = h->march_h_smem ? h_all : 0;
-    const size_t slot_bytes = march_slot_bytes(n, sched.rows, h->march_nv);
+    const size_t slot_bytes = march_slot_bytes(n, sched.rows, h->march_nv, F);
     const size_t sm_total = (size_t)max_optin, sm_half = (228 * 1024) / 2 - 2048;
     auto ring_for = [&](size_t budget, bool stage, int *ring) {
         const size_t fixed = (stage ? stage_bytes : 0) + 64;
-        for (int r = 16; r >= 4; --r)
+        // mbarrier parity waits are only valid within one phase of the barrier: a slot is always refilled by the same producer
+        // warp (ring size a multiple of the producer warps per role) and the ring holds at least one tile per consumer warp
+        for (int r = 16; r >= march_consumers(n); r -= 2)
             if (fixed + march_meta_bytes(sched.max_levels, noc, r, h_doubles) + (size_t)r * slot_bytes <= budget)
             {
                 *ring = r;
@@ -497,7 +507,7 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
         return false;
     };
     int ring = 0;
-    if (ring_for(sm_half, true, &ring) && ring >= 6) h->march_stage = true;
+    if (ring_for(sm_half, true, &ring)) h->march_stage = true;
     else if (ring_for(sm_total - 1024, true, &ring)) h->march_stage = true;
     else if (ring_for(sm_half, false, &ring) || ring_for(sm_total - 1024, false, &ring)) h->march_stage = false;
     else return fail(PBTE_ERR_INVALID, "marching kernel does not fit in shared memory for this ndof / level count");

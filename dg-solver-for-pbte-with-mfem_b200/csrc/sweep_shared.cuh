@@ -39,7 +39,7 @@ struct DevMarch
     const unsigned long long *slot_op_base;  // [nslots] offset (doubles) of the slot's operator block in ops
     double *ops;                      // operators in MMA fragment order
     double *oph;                      // [nslots][noclass][F][n] wall vectors h_f
-    const double *ctbc;               // [ne][F] wall temperature per canonical face
+    const double *ctbc;               // [ne][Fp] wall temperature per canonical face, Fp = F rounded up to even (16-byte rows)
     // operator construction
     const int32_t *oc_rep;            // [noclass]
     const int32_t *oc_ksrc, *oc_gsrc; // [noclass][F] element*F + local face, or -1
@@ -52,10 +52,11 @@ template <int N>
 struct Frag
 {
     static constexpr int MT = (N + 7) / 8;   // 8-row blocks of the operator
+    static constexpr int MP = (MT + 1) / 2;  // pairs of row blocks: one 16-byte shared-memory load feeds two MMAs
     static constexpr int KS = (N + 3) / 4;   // k steps of 4
-    static constexpr int FR = MT * KS * 32;  // doubles per operator in fragment order
+    static constexpr int FR = MP * KS * 64;  // doubles per operator in fragment order
 };
-__host__ __device__ inline int frag_doubles(int n) { return ((n + 7) / 8) * ((n + 3) / 4) * 32; }
+__host__ __device__ inline int frag_doubles(int n) { return ((((n + 7) / 8) + 1) / 2) * ((n + 3) / 4) * 64; }
 
 // thread j solves column j of R in place with the row-pivoted LU factors in A (swaps, unit-lower forward, upper backward)
 __device__ __forceinline__ void lu_solve_columns(const double *A, double *R, const int *piv, int n, int ncol)
@@ -86,15 +87,17 @@ __device__ __forceinline__ void lu_solve_columns(const double *A, double *R, con
     }
 }
 
-// out[(I*KS + kk)*32 + lane] = R[8I + lane/4][4kk + lane%4] (zero padded): the B fragments of mma m8n8k4 for R^T
+// Fragment order of an operator R (n x n, column-major): the B fragment of mma m8n8k4 for row block I and k block kk holds
+// R[8I + lane/4][4kk + lane%4] in lane `lane`; row blocks are stored in pairs so that lane `lane` finds the fragments of
+// blocks 2Ip and 2Ip+1 in one 16-byte word:  out[((Ip*KS + kk)*32 + lane)*2 + (I & 1)], zero padded.
 __device__ __forceinline__ void store_fragment_order(double *out, const double *R, int n)
 {
-    const int KS = (n + 3) / 4, FR = frag_doubles(n);
+    const int MT = (n + 7) / 8, KS = (n + 3) / 4, FR = frag_doubles(n);
     for (int idx = threadIdx.x; idx < FR; idx += blockDim.x)
     {
-        const int lane = idx & 31, blk = idx >> 5, kk = blk % KS, I = blk / KS;
+        const int half = idx & 1, lane = (idx >> 1) & 31, blk = idx >> 6, kk = blk % KS, I = 2 * (blk / KS) + half;
         const int row = 8 * I + (lane >> 2), col = 4 * kk + (lane & 3);
-        out[idx] = (row < n && col < n) ? R[row + (size_t)col * n] : 0.0;
+        out[idx] = (I < MT && row < n && col < n) ? R[row + (size_t)col * n] : 0.0;
     }
 }
 
@@ -237,7 +240,7 @@ __global__ void __launch_bounds__(128) build_operators_kernel(DevProblem P, DevM
 // d0,d1 = D[lane/4][2*(lane%4) + {0,1}].
 __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b)
 {
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -320,10 +323,13 @@ __device__ __forceinline__ void cp_async_arrive(uint64_t *bar)
 }
 
 constexpr int kMaxIn = 4;          // inflow faces whose wall temperature a consumer lane prefetches (tri 2, quad/hex dim, tet 3)
-constexpr int kConsumerWarps = 4;  // one MMA warp per SM sub-partition
+// MMA (consumer) warps of a marching CTA: two per SM sub-partition, so that one covers the other's descriptor / wall / store
+// phases; one per sub-partition for large elements (registers, and the ring must hold at least one tile per consumer)
+__host__ __device__ constexpr int march_consumers(int n) { return n <= 36 ? 8 : 4; }
 constexpr int kSrcWarps = 2;       // source loaders (run ahead of the wavefront); warp p takes tiles p, p + kSrcWarps, ...
 constexpr int kNbrWarps = 2;       // upwind-neighbour loaders (follow the wavefront), same interleaving
-constexpr int kMarchThreads = (kConsumerWarps + kSrcWarps + kNbrWarps) * 32;
+static_assert(kSrcWarps == 2 && kNbrWarps == 2, "ring sizes are chosen even so that every slot has one producer warp per role");
+__host__ __device__ constexpr int march_threads(int n) { return (march_consumers(n) + kSrcWarps + kNbrWarps) * 32; }
 
 // shared-memory row stride (doubles) of a staged element vector: 4*KS rounded so that the four element rows a half warp reads
 // with one LDS.64 fall into disjoint bank groups (stride mod 16 in {4, 12})
@@ -332,8 +338,11 @@ __host__ __device__ constexpr int stage_stride(int n)
     const int ns = ((n + 3) / 4) * 4;
     return (ns % 16 == 0 || ns % 16 == 8) ? ns + 4 : ns;
 }
-// bytes of one ring slot: tile descriptor (rows x 8 int32) + nv staged vectors of 8 elements
-__host__ __device__ inline size_t march_slot_bytes(int n, int rows, int nv) { return (size_t)rows * 32 + (size_t)nv * kTile * stage_stride(n) * sizeof(double); }
+// bytes of one ring slot: tile descriptor (rows x 8 int32) + wall temperatures (8 x Fp) + nv staged vectors of 8 elements
+__host__ __device__ inline size_t march_slot_bytes(int n, int rows, int nv, int F)
+{
+    return (size_t)rows * 32 + (size_t)kTile * ((F + 1) & ~1) * sizeof(double) + (size_t)nv * kTile * stage_stride(n) * sizeof(double);
+}
 // bytes of metadata and barriers: level offsets, inflow masks, operator offsets; full/empty per ring slot, one barrier per level;
 // h_doubles wall-vector entries staged when they fit
 __host__ __device__ inline size_t march_meta_bytes(int max_levels, int noclass, int ring, size_t h_doubles)
@@ -343,7 +352,7 @@ __host__ __device__ inline size_t march_meta_bytes(int max_levels, int noclass, 
     return ints * sizeof(int32_t) + sizeof(uint64_t) * (2 * (size_t)ring + (size_t)max_levels) + sizeof(double) * h_doubles;
 }
 
-// grid = nslots CTAs of kMarchThreads threads.  Dynamic shared memory = [operators (STAGE) | metadata | barriers | tile ring].
+// grid = nslots CTAs of march_threads(N) threads.  Dynamic shared memory = [operators (STAGE) | metadata | barriers | tile ring].
 //
 // Warp-specialised pipeline over the slot's tile sequence i = 0 .. NT-1 (level-major, so round-robin assignment keeps the
 // consumers balanced inside every level); ring slot = i mod R:
@@ -355,10 +364,11 @@ __host__ __device__ inline size_t march_meta_bytes(int max_levels, int noclass, 
 //                     fragments from the ring and B fragments from the staged operators; releases empty[slot]; adds wall
 //                     terms, stores the tile, arrives on the barrier of its level.
 template <int N, bool STAGE>
-__global__ void __launch_bounds__(kMarchThreads, 2) sweep_march_kernel(DevProblem P, DevMarch S)
+__global__ void __launch_bounds__(march_threads(N), N <= 36 ? 2 : 1) sweep_march_kernel(DevProblem P, DevMarch S)
 {
+    constexpr int kConsumerWarps = march_consumers(N);
     using G = Frag<N>;
-    constexpr int MT = G::MT, KS = G::KS, FR = G::FR;
+    constexpr int MT = G::MT, MP = G::MP, KS = G::KS, FR = G::FR;
     constexpr int NP = (N + 1) & ~1;        // global row stride (doubles): 16-byte aligned rows
     constexpr int NS = stage_stride(N);     // shared-memory row stride
     constexpr int CH = NP / 2;              // 16-byte chunks per row
@@ -380,7 +390,9 @@ __global__ void __launch_bounds__(kMarchThreads, 2) sweep_march_kernel(DevProble
     uint64_t *full = reinterpret_cast<uint64_t *>(sm_raw + op_bytes + meta_ints * sizeof(int32_t));  // [R]
     uint64_t *empty = full + R;                                                                     // [R]
     uint64_t *level_bar = empty + R;                                                                // [nlev]
-    const size_t slot_bytes = (size_t)rows * 32 + (size_t)nv * kTile * NS * sizeof(double);
+    const int Fp = (F + 1) & ~1;
+    const size_t hdr_bytes = (size_t)rows * 32 + (size_t)kTile * Fp * sizeof(double);  // descriptor + wall temperatures
+    const size_t slot_bytes = hdr_bytes + (size_t)nv * kTile * NS * sizeof(double);
     double *s_h = reinterpret_cast<double *>(level_bar + nlev);  // [noclass][F][N] wall vectors of this slot (when S.h_smem)
     const size_t h_doubles = S.h_smem ? (size_t)noc * F * N : 0;
     unsigned char *ring = reinterpret_cast<unsigned char *>(s_h + h_doubles);
@@ -449,7 +461,7 @@ __global__ void __launch_bounds__(kMarchThreads, 2) sweep_march_kernel(DevProble
             if (i + kSrcWarps < NT) e_next = __ldg(desc_g + (size_t)kSrcWarps * rows * kTile + q);
             if (it > 0) mbar_wait(empty + slot, (it - 1) & 1);
             unsigned char *sl = ring + (size_t)slot * slot_bytes;
-            const uint32_t vb = smem_u32(sl + rows * 32);
+            const uint32_t vb = smem_u32(sl + hdr_bytes);
 #pragma unroll
             for (int k = 0; k < IT; ++k)
             {
@@ -462,6 +474,13 @@ __global__ void __launch_bounds__(kMarchThreads, 2) sweep_march_kernel(DevProble
                 }
             }
             if (lane < rows * 2) cp_async16(sl + lane * 16, reinterpret_cast<const unsigned char *>(desc_g) + lane * 16, 16u);
+            {
+                // wall temperatures of the 8 elements: Fp/2 chunks per row (at most 32 chunks in all)
+                const int hc = Fp >> 1, row = lane / hc, ch = lane - row * hc;
+                const int er = __shfl_sync(0xffffffffu, e, row & 7);
+                if (lane < kTile * hc)
+                    cp_async16(sl + rows * 32 + lane * 16, S.ctbc + (size_t)(er < 0 ? 0 : er) * Fp + 2 * ch, er >= 0 ? 16u : 0u);
+            }
             cp_async_arrive(full + slot);
         }
     }
@@ -504,7 +523,7 @@ __global__ void __launch_bounds__(kMarchThreads, 2) sweep_march_kernel(DevProble
                 // lane (mq, q) holds the source code of row mq*8 + q of this pass
                 const int code = m0 == 0 ? code0 : ((m0 + mq < nin) ? __ldg(desc_g + (1 + m0 + mq) * kTile + q) : kSrcSkipCode);
                 const int nrow = min(nin - m0, 4) * kTile;
-                const uint32_t vb = smem_u32(sl + rows * 32) + (uint32_t)((2 + m0) * kTile * NS * 8);
+                const uint32_t vb = smem_u32(sl + hdr_bytes) + (uint32_t)((2 + m0) * kTile * NS * 8);
 #pragma unroll
                 for (int k = 0; k < IT; ++k)
                 {
@@ -531,69 +550,58 @@ __global__ void __launch_bounds__(kMarchThreads, 2) sweep_march_kernel(DevProble
             const int slot = i % R, it = i / R;
             const unsigned char *sl = ring + (size_t)slot * slot_bytes;
             const int32_t *sd = reinterpret_cast<const int32_t *>(sl);
-            const double *vec = reinterpret_cast<const double *>(sl + rows * 32) + (size_t)q * NS + r;
+            const double *vec = reinterpret_cast<const double *>(sl + hdr_bytes) + (size_t)q * NS + r;
             mbar_wait(full + slot, it & 1);
             const int e = sd[q], o = sd[(1 + F) * kTile], L = sd[(1 + F) * kTile + 1];
             const unsigned inm = (unsigned)s_inm[o];
             const int nin = __popc(inm);
             const double *op = ops + (size_t)s_opoff[o] * FR;
-            // wall temperatures of this lane's element are fetched now and used after the MMAs (their L2 latency is hidden)
+            // source codes of the first kMaxIn inflow faces (rows 1..4 of the descriptor always exist): wall faces of this lane
             unsigned wall = 0;
-            double tb[kMaxIn];
-            {
-                unsigned rest = inm;
 #pragma unroll
-                for (int m = 0; m < kMaxIn; ++m)
-                {
-                    tb[m] = 0.0;
-                    if (rest)
-                    {
-                        if (sd[(1 + m) * kTile + q] == kSrcWallCode)
-                        {
-                            wall |= 1u << m;
-                            tb[m] = __ldg(S.ctbc + (size_t)e * F + (__ffs(rest) - 1));
-                        }
-                        rest &= rest - 1;
-                    }
-                }
-            }
+            for (int m = 0; m < kMaxIn; ++m) wall |= (unsigned)(sd[(1 + m) * kTile + q] == kSrcWallCode && m < nin) << m;
+            const double *tbq = reinterpret_cast<const double *>(sl + rows * 32) + (size_t)q * Fp;  // wall temperatures of element q
             double acc[MT][2];
 #pragma unroll
             for (int I = 0; I < MT; ++I) acc[I][0] = acc[I][1] = 0.0;
-            // source / pseudo-time term: X = c1 T_old + c2 u_old
+            // One matrix block = KS k steps of MT MMAs: A fragment from the staged vector, B fragments (two row blocks per 16-byte
+            // load) from the staged operator.  The fragments of KC k steps are loaded together into their own registers and
+            // only then multiplied: no register is rewritten while MMAs that read it are in flight and every MMA finds its
+            // operands ready, so a warp that is alone on its sub-partition issues at the pipe rate (interleaved load/MMA code
+            // ran at the MMA latency, 26 cycles per MMA instead of 16: tools/dmma_probe.cu, per-tile timeline in profiles/).
+            constexpr int KC = (16 / (2 * MP)) < 1 ? 1 : (16 / (2 * MP) > KS ? KS : 16 / (2 * MP));
+            auto block = [&](const double *va, const double *vt, const double *opb) {
+                const double2 *bp = reinterpret_cast<const double2 *>(opb) + lane;
 #pragma unroll
-            for (int kk = 0; kk < KS; ++kk)
-            {
-                const double x = fma(c2, vec[4 * kk], c1 * vec[(size_t)kTile * NS + 4 * kk]);
-#pragma unroll
-                for (int I = 0; I < MT; ++I)
+                for (int k0 = 0; k0 < KS; k0 += KC)
                 {
-                    const double b = STAGE ? op[(I * KS + kk) * 32 + lane] : __ldg(op + (I * KS + kk) * 32 + lane);
-                    dmma_m8n8k4(acc[I][0], acc[I][1], x, b);
+                    double2 bq[KC][MP];
+                    double xa[KC];
+#pragma unroll
+                    for (int k = 0; k < KC; ++k)
+                        if (k0 + k < KS)
+                        {
+#pragma unroll
+                            for (int Ip = 0; Ip < MP; ++Ip) bq[k][Ip] = STAGE ? bp[(Ip * KS + k0 + k) * 32] : __ldg(bp + (Ip * KS + k0 + k) * 32);
+                            xa[k] = vt ? fma(c2, va[4 * (k0 + k)], c1 * vt[4 * (k0 + k)]) : va[4 * (k0 + k)];
+                        }
+#pragma unroll
+                    for (int k = 0; k < KC; ++k)
+                        if (k0 + k < KS)
+                        {
+#pragma unroll
+                            for (int I = 0; I < MT; ++I) dmma_m8n8k4(acc[I][0], acc[I][1], xa[k], (I & 1) ? bq[k][I >> 1].y : bq[k][I >> 1].x);
+                        }
                 }
-            }
-            // upwind couplings of the inflow faces
+            };
+            block(vec, vec + (size_t)kTile * NS, op);  // source / pseudo-time term: X = c1 T_old + c2 u_old
             for (int m = 0; m < nin; ++m)
             {
                 const int code = sd[(1 + m) * kTile + q];
                 if (m >= kMaxIn && code == kSrcWallCode) wall |= 1u << m;
-                if (__ballot_sync(0xffffffffu, code >= 0) == 0u) continue;
-                const double *vm = vec + (size_t)(2 + m) * kTile * NS;
-                const double *oq = op + (size_t)(1 + m) * FR;
-#pragma unroll
-                for (int kk = 0; kk < KS; ++kk)
-                {
-                    const double x = vm[4 * kk];
-#pragma unroll
-                    for (int I = 0; I < MT; ++I)
-                    {
-                        const double b = STAGE ? oq[(I * KS + kk) * 32 + lane] : __ldg(oq + (I * KS + kk) * 32 + lane);
-                        dmma_m8n8k4(acc[I][0], acc[I][1], x, b);
-                    }
-                }
+                if (__ballot_sync(0xffffffffu, code >= 0) == 0u) continue;  // no lane has an interior upwind neighbour on this face
+                block(vec + (size_t)(2 + m) * kTile * NS, nullptr, op + (size_t)(1 + m) * FR);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + slot);  // every staged value of the tile has been consumed by an MMA
             // isothermal walls on inflow faces: + T_bc h_j   (this lane owns element q, dofs 8I + 2r + {0,1})
             if (wall)
             {
@@ -608,16 +616,11 @@ __global__ void __launch_bounds__(kMarchThreads, 2) sweep_march_kernel(DevProble
                     }
                 };
                 unsigned rest = inm;
-#pragma unroll
-                for (int m = 0; m < kMaxIn; ++m)
-                    if (rest)
-                    {
-                        if (wall >> m & 1u) add_wall(__ffs(rest) - 1, tb[m]);
-                        rest &= rest - 1;
-                    }
-                for (int m = kMaxIn; rest; ++m, rest &= rest - 1)
-                    if (wall >> m & 1u) add_wall(__ffs(rest) - 1, __ldg(S.ctbc + (size_t)e * F + (__ffs(rest) - 1)));
+                for (int m = 0; rest; ++m, rest &= rest - 1)
+                    if (wall >> m & 1u) add_wall(__ffs(rest) - 1, tbq[__ffs(rest) - 1]);
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + slot);  // every staged value of the tile (vectors, wall temperatures) has been consumed
             if (e >= 0)
             {
                 double *dst = u + (size_t)e * NP;
