@@ -281,20 +281,18 @@ def run_gpu(args, rank, world, local_rank):
     #   out: Tc, Qc, Tv, Qv and the residual back to host               (pbte_cuda_download_moments)
     # The flux is solver state and stays on the device, as in a Solve call of many iterations.
     block = P.ndof * P.ne
-    tc_host = torch.zeros(block, dtype=torch.float64).pin_memory()
-    tv_host = torch.zeros(P.ne, dtype=torch.float64).pin_memory()
-    m = solver.download_moments()
-    tc_host.copy_(torch.from_numpy(m["Tc"]))
-    tv_host.copy_(torch.from_numpy(m["Tv"]))
+    # pinned host buffers for everything that crosses the boundary (the C ABI takes plain host pointers)
+    pinned = {k: torch.zeros(shape, dtype=torch.float64).pin_memory()
+              for k, shape in (("Tc", (block,)), ("Qc", (P.dim, block)), ("Tv", (P.ne,)), ("Qv", (P.dim, P.ne)))}
+    host = {k: v.numpy() for k, v in pinned.items()}
+    solver.download_moments(host)
     barrier()
     t0 = time.perf_counter()
     with torch.cuda.stream(stream):
         for _ in range(args.steps):
-            solver.upload_moments(tc_host.numpy(), tv_host.numpy())
+            solver.upload_moments(host["Tc"], host["Tv"])   # previous iterate from host memory
             res = step()
-            m = solver.download_moments()
-            tc_host.copy_(torch.from_numpy(m["Tc"]))
-            tv_host.copy_(torch.from_numpy(m["Tv"]))
+            solver.download_moments(host)                    # Tc, Qc, Tv, Qv back to host memory (synchronises)
     barrier()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")

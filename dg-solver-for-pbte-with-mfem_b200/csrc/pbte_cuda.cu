@@ -490,7 +490,9 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
     // that leaves room for a ring of >= 6 tiles each, one CTA otherwise; without room for operators they are read through L1.
     h->march_nv = 2 + sched.max_inflow;
     const size_t h_all = (size_t)noc * F * n;
-    h->march_h_smem = h_all * sizeof(double) <= 16 * 1024;
+    // PBTE_MARCH_NOSTAGE=1 forces the large-mesh code path (operators and wall vectors read through L1 instead of staged)
+    const bool allow_stage = !(std::getenv("PBTE_MARCH_NOSTAGE") && std::atoi(std::getenv("PBTE_MARCH_NOSTAGE")) != 0);
+    h->march_h_smem = allow_stage && h_all * sizeof(double) <= 16 * 1024;
     const size_t h_doubles = h->march_h_smem ? h_all : 0;
     const size_t slot_bytes = march_slot_bytes(n, sched.rows, h->march_nv, F);
     const size_t sm_total = (size_t)max_optin, sm_half = (228 * 1024) / 2 - 2048;
@@ -507,8 +509,8 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
         return false;
     };
     int ring = 0;
-    if (ring_for(sm_half, true, &ring)) h->march_stage = true;
-    else if (ring_for(sm_total - 1024, true, &ring)) h->march_stage = true;
+    if (allow_stage && ring_for(sm_half, true, &ring)) h->march_stage = true;
+    else if (allow_stage && ring_for(sm_total - 1024, true, &ring)) h->march_stage = true;
     else if (ring_for(sm_half, false, &ring) || ring_for(sm_total - 1024, false, &ring)) h->march_stage = false;
     else return fail(PBTE_ERR_INVALID, "marching kernel does not fit in shared memory for this ndof / level count");
     h->march_ring = ring;

@@ -398,10 +398,12 @@ class Solver:
         Tv = None if Tv is None else np.ascontiguousarray(Tv, dtype=np.float64)
         _ck(self.lib.pbte_cuda_upload_moments(self._h, _dp(Tc), _dp(Tv)))
 
-    def download_moments(self):
+    def download_moments(self, out=None):
+        """Tc, Qc, Tv, Qv of the last iteration; `out` may hold preallocated (e.g. pinned) float64 arrays of the right sizes."""
         p = self.problem
         block = p.ndof * p.ne
-        out = dict(Tc=np.zeros(block), Qc=np.zeros((p.dim, block)), Tv=np.zeros(p.ne), Qv=np.zeros((p.dim, p.ne)))
+        if out is None:
+            out = dict(Tc=np.zeros(block), Qc=np.zeros((p.dim, block)), Tv=np.zeros(p.ne), Qv=np.zeros((p.dim, p.ne)))
         _ck(self.lib.pbte_cuda_download_moments(self._h, _dp(out["Tc"]), _dp(out["Qc"]), _dp(out["Tv"]), _dp(out["Qv"])))
         return out
 
