@@ -282,9 +282,10 @@ def run_gpu(args, rank, world, local_rank):
     # The flux is solver state and stays on the device, as in a Solve call of many iterations.
     block = P.ndof * P.ne
     # pinned host buffers for everything that crosses the boundary (the C ABI takes plain host pointers)
-    pinned = {k: torch.zeros(shape, dtype=torch.float64).pin_memory()
-              for k, shape in (("Tc", (block,)), ("Qc", (P.dim, block)), ("Tv", (P.ne,)), ("Qv", (P.dim, P.ne)))}
-    host = {k: v.numpy() for k, v in pinned.items()}
+    pin_m = torch.zeros((1 + P.dim) * block, dtype=torch.float64).pin_memory()   # [Tc | Qc] as the library holds them
+    pin_c = torch.zeros((1 + P.dim) * P.ne, dtype=torch.float64).pin_memory()    # [Tv | Qv]
+    hm, hcell = pin_m.numpy(), pin_c.numpy()
+    host = {"Tc": hm[:block], "Qc": hm[block:].reshape(P.dim, block), "Tv": hcell[: P.ne], "Qv": hcell[P.ne:].reshape(P.dim, P.ne)}
     solver.download_moments(host)
     barrier()
     t0 = time.perf_counter()

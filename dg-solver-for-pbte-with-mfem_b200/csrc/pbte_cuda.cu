@@ -501,7 +501,7 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
         // mbarrier parity waits are only valid within one phase of the barrier: a slot is always refilled by the same producer
         // warp (ring size a multiple of the producer warps per role) and the ring holds at least one tile per consumer warp
         for (int r = 16; r >= march_consumers(n); r -= 2)
-            if (fixed + march_meta_bytes(sched.max_levels, noc, r, h_doubles) + (size_t)r * slot_bytes <= budget)
+            if (fixed + march_meta_bytes(sched.max_levels, noc, r, sched.max_class_tiles, h_doubles) + (size_t)r * slot_bytes <= budget)
             {
                 *ring = r;
                 return true;
@@ -514,7 +514,7 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
     else if (ring_for(sm_half, false, &ring) || ring_for(sm_total - 1024, false, &ring)) h->march_stage = false;
     else return fail(PBTE_ERR_INVALID, "marching kernel does not fit in shared memory for this ndof / level count");
     h->march_ring = ring;
-    h->march_smem = (h->march_stage ? stage_bytes : 0) + 64 + march_meta_bytes(sched.max_levels, noc, ring, h_doubles) + (size_t)ring * slot_bytes;
+    h->march_smem = (h->march_stage ? stage_bytes : 0) + 64 + march_meta_bytes(sched.max_levels, noc, ring, sched.max_class_tiles, h_doubles) + (size_t)ring * slot_bytes;
     MarchKernelFn fn = pick_march_kernel(n, h->march_stage);
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->march_smem));
 
@@ -1065,14 +1065,15 @@ int pbte_cuda_upload_moments(pbte_handle_t *h, const double *Tc, const double *T
     const size_t block = (size_t)h->ne * h->n;
     if (Tc)
     {
-        CK(cudaMemcpy2DAsync(h->tc_prev.p, h->np * sizeof(double), Tc, h->n * sizeof(double), h->n * sizeof(double), h->ne, cudaMemcpyHostToDevice,
-                             h->stream));
+        // one contiguous host-to-device copy; the padded copy for the sweep is made on the device
         CK(cudaMemcpyAsync(h->mom.p, Tc, block * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpy2DAsync(h->tc_prev.p, h->np * sizeof(double), h->mom.p, h->n * sizeof(double), h->n * sizeof(double), h->ne,
+                             cudaMemcpyDeviceToDevice, h->stream));
     }
     if (Tv)
     {
-        CK(cudaMemcpyAsync(h->tv_prev.p, Tv, h->ne * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(h->cell.p, Tv, h->ne * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->tv_prev.p, h->cell.p, h->ne * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     }
     CK(cudaStreamSynchronize(h->stream));
     return PBTE_OK;
@@ -1085,10 +1086,18 @@ int pbte_cuda_download_moments(pbte_handle_t *h, double *Tc, double *Qc, double 
     if (!h->mom.p) return fail(PBTE_ERR_STATE, "handle holds no moment state");
     DeviceGuard guard(h->device);
     const size_t block = (size_t)h->ne * h->n;
-    if (Tc) CK(cudaMemcpyAsync(Tc, h->mom.p, block * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (Qc) CK(cudaMemcpyAsync(Qc, h->mom.p + block, h->dim * block * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (Tv) CK(cudaMemcpyAsync(Tv, h->cell.p, h->ne * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (Qv) CK(cudaMemcpyAsync(Qv, h->cell.p + h->ne, (size_t)h->dim * h->ne * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (Tc && Qc && Qc == Tc + block) CK(cudaMemcpyAsync(Tc, h->mom.p, (1 + h->dim) * block * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    else
+    {
+        if (Tc) CK(cudaMemcpyAsync(Tc, h->mom.p, block * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (Qc) CK(cudaMemcpyAsync(Qc, h->mom.p + block, h->dim * block * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (Tv && Qv && Qv == Tv + h->ne) CK(cudaMemcpyAsync(Tv, h->cell.p, (size_t)(1 + h->dim) * h->ne * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    else
+    {
+        if (Tv) CK(cudaMemcpyAsync(Tv, h->cell.p, h->ne * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (Qv) CK(cudaMemcpyAsync(Qv, h->cell.p + h->ne, (size_t)h->dim * h->ne * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
     CK(cudaStreamSynchronize(h->stream));
     return PBTE_OK;
 }

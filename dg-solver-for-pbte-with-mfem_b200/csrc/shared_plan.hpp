@@ -268,11 +268,14 @@ inline SharedPlan classify_elements(const pbte_problem_t &p, double tol = 1e-12,
 struct MarchSchedule
 {
     int nclass = 0, F = 0, rows = 0, ntiles = 0, max_levels = 0, max_inflow = 0;  // rows = 2 + F descriptor rows of 8 ints per tile
+    int max_class_tiles = 0;               // most tiles of any DAG class
     std::vector<int32_t> cls_level_begin;  // [nclass+1] into level_tile_begin (class c has cls_level_begin[c+1]-cls_level_begin[c]-1 levels)
     std::vector<int32_t> level_tile_begin; // per class: nlevels+1 tile offsets (global tile indices)
     std::vector<int32_t> tile_oclass;      // [ntiles]
     std::vector<int32_t> tile_desc;        // [ntiles][2+F][8]: row 0 = elements (-1 padding), row 1+m = source of the m-th inflow face of the
-                                           // tile's class, row 1+F = header {operator class, level, tile index in class, 0...}
+                                           // tile's class, row 1+F = header {operator class, level, tile index in class, last
+                                           // prerequisite tile (index in class; -1 none), 0...}: every upwind neighbour of the tile's
+                                           // elements lies in a tile with an index <= that
     std::vector<uint8_t> cls_inmask;       // [nclass][noclass] canonical inflow faces (interior or wall) of the class representative
     double fill = 0.0;                     // elements / (8 * tiles)
 };
@@ -358,6 +361,30 @@ inline MarchSchedule build_march_schedule(const SharedPlan &plan, int nclass, co
             ++S.ntiles;
         }
         while (cur_level < nlev) ltb[++cur_level] = S.ntiles;
+        // last prerequisite tile of every tile of this class
+        {
+            const int t_begin = ltb[0], t_end = S.ntiles;
+            S.max_class_tiles = std::max(S.max_class_tiles, t_end - t_begin);
+            std::vector<int32_t> tile_of(ne, -1);
+            for (int t = t_begin; t < t_end; ++t)
+                for (int k = 0; k < kTileElems; ++k)
+                {
+                    const int e = S.tile_desc[(size_t)t * rows * kTileElems + k];
+                    if (e >= 0) tile_of[e] = t - t_begin;
+                }
+            for (int t = t_begin; t < t_end; ++t)
+            {
+                int32_t *d = S.tile_desc.data() + (size_t)t * rows * kTileElems;
+                int dep = -1;
+                for (int m = 0; m < F; ++m)
+                    for (int k = 0; k < kTileElems; ++k)
+                    {
+                        const int code = d[(size_t)(1 + m) * kTileElems + k];
+                        if (code >= 0) dep = std::max(dep, (int)tile_of[code]);
+                    }
+                d[(size_t)(1 + F) * kTileElems + 3] = dep;
+            }
+        }
     }
     S.fill = S.ntiles ? (double)nclass * ne / ((double)kTileElems * S.ntiles) : 0.0;
     return S;

@@ -343,13 +343,13 @@ __host__ __device__ inline size_t march_slot_bytes(int n, int rows, int nv, int 
 {
     return (size_t)rows * 32 + (size_t)kTile * ((F + 1) & ~1) * sizeof(double) + (size_t)nv * kTile * stage_stride(n) * sizeof(double);
 }
-// bytes of metadata and barriers: level offsets, inflow masks, operator offsets; full/empty per ring slot, one barrier per level;
-// h_doubles wall-vector entries staged when they fit
-__host__ __device__ inline size_t march_meta_bytes(int max_levels, int noclass, int ring, size_t h_doubles)
+// bytes of metadata and barriers: level offsets, inflow masks, operator offsets; full/empty per ring slot; the bitmap of finished
+// tiles; h_doubles wall-vector entries staged when they fit
+__host__ __device__ inline size_t march_meta_bytes(int max_levels, int noclass, int ring, int max_class_tiles, size_t h_doubles)
 {
-    size_t ints = (size_t)max_levels + 1 + 2 * (size_t)noclass;
+    size_t ints = (size_t)max_levels + 1 + 2 * (size_t)noclass + (size_t)(max_class_tiles + 31) / 32 + 1;
     ints = (ints + 3) & ~(size_t)3;
-    return ints * sizeof(int32_t) + sizeof(uint64_t) * (2 * (size_t)ring + (size_t)max_levels) + sizeof(double) * h_doubles;
+    return ints * sizeof(int32_t) + sizeof(uint64_t) * (2 * (size_t)ring) + sizeof(double) * h_doubles;
 }
 
 // grid = nslots CTAs of march_threads(N) threads.  Dynamic shared memory = [operators (STAGE) | metadata | barriers | tile ring].
@@ -358,11 +358,13 @@ __host__ __device__ inline size_t march_meta_bytes(int max_levels, int noclass, 
 // consumers balanced inside every level); ring slot = i mod R:
 //   source producer   waits empty[slot]; cp.async of the tile descriptor and of the u_old / T_old rows of its 8 elements.
 //                     Independent of the current sweep: runs up to R tiles ahead and hides the HBM latency.
-//   neighbour producer waits empty[slot] and the barrier of the previous level (all its tiles stored); cp.async of the upwind
-//                     neighbour rows (L2 hits: written by this CTA a level ago).  Both producers complete full[slot].
+//   neighbour producer waits empty[slot] and until every tile up to the tile's last prerequisite (descriptor header) is stored:
+//                     consumers set a bit per finished tile, the producer advances a watermark over the bitmap (no level-wide
+//                     barrier: tiles of the next level start as soon as their own upwind tiles are done); cp.async of the
+//                     upwind neighbour rows (L2 hits: written by this CTA a level ago).  Both producers complete full[slot].
 //   consumer w        tiles i = w mod 4: waits full[slot]; U = X P^T + sum_m Unbr_m Q_m^T by mma.sync m8n8k4 FP64 with A
 //                     fragments from the ring and B fragments from the staged operators; releases empty[slot]; adds wall
-//                     terms, stores the tile, arrives on the barrier of its level.
+//                     terms, stores the tile, sets its bit in the bitmap (release).
 template <int N, bool STAGE>
 __global__ void __launch_bounds__(march_threads(N), N <= 36 ? 2 : 1) sweep_march_kernel(DevProblem P, DevMarch S)
 {
@@ -386,20 +388,23 @@ __global__ void __launch_bounds__(march_threads(N), N <= 36 ? 2 : 1) sweep_march
     int32_t *ltb = reinterpret_cast<int32_t *>(sm_raw + op_bytes);  // [nlev+1] tile offsets of the levels
     int32_t *s_inm = ltb + nlev + 1;                                 // [noclass] inflow masks
     int32_t *s_opoff = s_inm + noc;                                  // [noclass] operator offsets (units of FR)
-    const size_t meta_ints = ((size_t)nlev + 1 + 2 * (size_t)noc + 3) & ~(size_t)3;
+    const int tbase0 = S.level_tile_begin[lb], NT0 = S.level_tile_begin[lb + nlev] - tbase0;
+    const int nwords = (NT0 + 31) / 32 + 1;
+    unsigned *s_done = reinterpret_cast<unsigned *>(s_opoff + noc);  // bit i: tile i of this class is stored
+    const size_t meta_ints = ((size_t)nlev + 1 + 2 * (size_t)noc + (size_t)nwords + 3) & ~(size_t)3;
     uint64_t *full = reinterpret_cast<uint64_t *>(sm_raw + op_bytes + meta_ints * sizeof(int32_t));  // [R]
     uint64_t *empty = full + R;                                                                     // [R]
-    uint64_t *level_bar = empty + R;                                                                // [nlev]
     const int Fp = (F + 1) & ~1;
     const size_t hdr_bytes = (size_t)rows * 32 + (size_t)kTile * Fp * sizeof(double);  // descriptor + wall temperatures
     const size_t slot_bytes = hdr_bytes + (size_t)nv * kTile * NS * sizeof(double);
-    double *s_h = reinterpret_cast<double *>(level_bar + nlev);  // [noclass][F][N] wall vectors of this slot (when S.h_smem)
+    double *s_h = reinterpret_cast<double *>(empty + R);  // [noclass][F][N] wall vectors of this slot (when S.h_smem)
     const size_t h_doubles = S.h_smem ? (size_t)noc * F * N : 0;
     unsigned char *ring = reinterpret_cast<unsigned char *>(s_h + h_doubles);
     ring = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(ring) + 15) & ~(uintptr_t)15);
     for (size_t i = threadIdx.x; i < h_doubles; i += blockDim.x) s_h[i] = S.oph[(size_t)s * noc * F * N + i];
 
     for (int i = threadIdx.x; i <= nlev; i += blockDim.x) ltb[i] = S.level_tile_begin[lb + i];
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) s_done[i] = 0u;
     for (int i = threadIdx.x; i < noc; i += blockDim.x)
     {
         s_inm[i] = S.cls_inmask[(size_t)c * noc + i];
@@ -408,14 +413,8 @@ __global__ void __launch_bounds__(march_threads(N), N <= 36 ? 2 : 1) sweep_march
     // the ring starts zeroed: copies write NP doubles per row, the k padding up to NS stays zero for the whole kernel
     for (size_t i = threadIdx.x; i < (size_t)R * slot_bytes / 16; i += blockDim.x) reinterpret_cast<uint4 *>(ring)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * R + nlev; i += blockDim.x)
-    {
-        uint32_t count;
-        if (i < R) count = 2 * 32;                                        // full: one source and one neighbour warp, every lane
-        else if (i < 2 * R) count = 1;                                    // empty: lane 0 of the consuming warp
-        else count = (uint32_t)(ltb[i - 2 * R + 1] - ltb[i - 2 * R]);       // level: lane 0 of the warp of every tile of the level
-        mbar_init(full + i, count);
-    }
+    for (int i = threadIdx.x; i < 2 * R; i += blockDim.x) mbar_init(full + i, i < R ? 2 * 32 : 1);  // full: one source and one neighbour warp,
+                                                                                                    // every lane; empty: lane 0 of the consumer
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (STAGE)
     {
@@ -493,29 +492,33 @@ __global__ void __launch_bounds__(march_threads(N), N <= 36 ? 2 : 1) sweep_march
         for (int k = 0; k < IT; ++k) pat[k] = pack_pattern(k * 32 + lane, 32);
         const unsigned char *ub = reinterpret_cast<const unsigned char *>(u);
         const int q = lane & 7, mq = lane >> 3;
-        int waited = -1;  // levels [0, waited] are known to be complete
+        int wm = 0;  // watermark: tiles [0, wm) of this class are known to be stored
         const int first = warp - kConsumerWarps - kSrcWarps;
         const int32_t *d0 = S.tile_desc + (size_t)(tbase + first) * rows * kTile;
-        int o_next = first < NT ? __ldg(d0 + (1 + F) * kTile) : 0, L_next = first < NT ? __ldg(d0 + (1 + F) * kTile + 1) : 0;
+        int o_next = first < NT ? __ldg(d0 + (1 + F) * kTile) : 0, L_next = first < NT ? __ldg(d0 + (1 + F) * kTile + 3) : -1;
         int code_next = first < NT ? __ldg(d0 + (1 + mq) * kTile + q) : -1;  // rows 1..4 always exist (rows = 2 + F, F >= 3)
         for (int i = first; i < NT; i += kNbrWarps)
         {
             const int slot = i % R, it = i / R;
-            const int o = o_next, L = L_next, code0 = code_next;
+            const int o = o_next, dep = L_next, code0 = code_next;
             const int32_t *desc_g = S.tile_desc + (size_t)(tbase + i) * rows * kTile;
             if (i + kNbrWarps < NT)
             {
                 const int32_t *dn = desc_g + (size_t)kNbrWarps * rows * kTile;
                 o_next = __ldg(dn + (1 + F) * kTile);
-                L_next = __ldg(dn + (1 + F) * kTile + 1);
+                L_next = __ldg(dn + (1 + F) * kTile + 3);
                 code_next = __ldg(dn + (1 + mq) * kTile + q);
             }
             if (it > 0) mbar_wait(empty + slot, (it - 1) & 1);
-            if (L - 1 > waited)
+            // every tile up to the last prerequisite must be stored: advance the watermark over the bitmap of finished tiles
+            while (wm <= dep)
             {
-                mbar_wait(level_bar + (L - 1), 0);  // every tile of the previous level (hence of all earlier ones) is stored
-                waited = L - 1;
+                const unsigned w = *reinterpret_cast<volatile unsigned *>(s_done + (wm >> 5)) >> (wm & 31);
+                const int ones = (~w == 0u) ? 32 : __ffs(~w) - 1;  // consecutive finished tiles starting at wm (zeros are shifted in)
+                if (ones == 0) __nanosleep(32);
+                else wm += min(ones, 32 - (wm & 31));
             }
+            __threadfence_block();  // acquire: the stores of those tiles are visible to the copies issued below
             const int nin = __popc((unsigned)s_inm[o]);
             unsigned char *sl = ring + (size_t)slot * slot_bytes;
             for (int m0 = 0; m0 < nin; m0 += 4)
@@ -552,7 +555,7 @@ __global__ void __launch_bounds__(march_threads(N), N <= 36 ? 2 : 1) sweep_march
             const int32_t *sd = reinterpret_cast<const int32_t *>(sl);
             const double *vec = reinterpret_cast<const double *>(sl + hdr_bytes) + (size_t)q * NS + r;
             mbar_wait(full + slot, it & 1);
-            const int e = sd[q], o = sd[(1 + F) * kTile], L = sd[(1 + F) * kTile + 1];
+            const int e = sd[q], o = sd[(1 + F) * kTile];
             const unsigned inm = (unsigned)s_inm[o];
             const int nin = __popc(inm);
             const double *op = ops + (size_t)s_opoff[o] * FR;
@@ -633,7 +636,11 @@ __global__ void __launch_bounds__(march_threads(N), N <= 36 ? 2 : 1) sweep_march
                 }
             }
             __syncwarp();  // orders the stores of all lanes before lane 0's release
-            if (lane == 0) mbar_arrive(level_bar + L);
+            if (lane == 0)
+            {
+                __threadfence_block();
+                atomicOr(s_done + (i >> 5), 1u << (i & 31));
+            }
         }
     }
 }

@@ -119,6 +119,27 @@ extern "C" int plan_check_run(const pbte_problem_t *p, double tol, int max_class
     }
     const MarchSchedule S = build_march_schedule(plan, nclass, level.data(), cin.data(), cbin.data());
     if (info) info[2] = nclass, info[3] = S.ntiles, info[4] = S.max_levels;
+    // descriptor headers: operator class, level, index in class, last prerequisite tile (strictly earlier, covers every neighbour)
+    for (int c = 0; c < nclass; ++c)
+    {
+        const int lb = S.cls_level_begin[c], nlev = S.cls_level_begin[c + 1] - lb - 1;
+        const int t_begin = S.level_tile_begin[lb], t_end = S.level_tile_begin[lb + nlev];
+        std::vector<int> tile_of(ne, -1);
+        for (int t = t_begin; t < t_end; ++t)
+            for (int k = 0; k < kTileElems; ++k)
+                if (S.tile_desc[(size_t)t * S.rows * kTileElems + k] >= 0) tile_of[S.tile_desc[(size_t)t * S.rows * kTileElems + k]] = t - t_begin;
+        for (int t = t_begin; t < t_end; ++t)
+        {
+            const int32_t *d = S.tile_desc.data() + (size_t)t * S.rows * kTileElems, *hdr = d + (size_t)(1 + F) * kTileElems;
+            if (hdr[0] != S.tile_oclass[t] || hdr[2] != t - t_begin || hdr[3] >= t - t_begin) return 4;
+            for (int m = 0; m < F; ++m)
+                for (int k = 0; k < kTileElems; ++k)
+                {
+                    const int code = d[(size_t)(1 + m) * kTileElems + k];
+                    if (code >= 0 && (tile_of[code] < 0 || tile_of[code] > hdr[3])) return 4;
+                }
+        }
+    }
     if (fill) *fill = S.fill;
 
     // slot tables
