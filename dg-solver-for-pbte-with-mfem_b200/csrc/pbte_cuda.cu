@@ -8,6 +8,7 @@
 #include "schedule.cuh"
 #include "shared_plan.hpp"
 #include "sweep_generic.cuh"
+#include "sweep_regop.cuh"
 #include "sweep_shared.cuh"
 #include "sweep_warp.cuh"
 
@@ -109,6 +110,8 @@ struct pbte_handle
     int march_ntiles = 0;
     double march_fill = 0.0;
     bool march_stage = false;
+    DevBuf<long long> m_trace;  // development builds only
+    bool march_regop = false;  // one operator class: operators in consumer registers (sweep_regop.cuh)
     int march_h_smem = 0;
     int march_ring = 0, march_nv = 0;  // tile-ring slots per CTA, staged vectors per slot
     int mom_chunks = 1;  // slot chunks of the moment pass
@@ -300,6 +303,7 @@ DevMarch make_dev_march(pbte_handle *h)
     S.oc_gsrc = h->m_oc_gsrc.p;
     S.cface = h->m_cface.p;
     S.cnbr = h->m_cnbr.p;
+    S.trace = h->m_trace.p;
     return S;
 }
 
@@ -334,6 +338,29 @@ MarchKernelFn pick_march_kernel(int n, bool stage)
     }
 }
 
+template <int N>
+MarchKernelFn pick_regop_n()
+{
+    if constexpr (regop_supported(N)) return sweep_march_regop_kernel<N>;
+    return nullptr;
+}
+
+MarchKernelFn pick_regop_kernel(int n)
+{
+    switch (n)
+    {
+        case 4: return pick_regop_n<4>();
+        case 8: return pick_regop_n<8>();
+        case 9: return pick_regop_n<9>();
+        case 16: return pick_regop_n<16>();
+        case 25: return pick_regop_n<25>();
+        case 27: return pick_regop_n<27>();
+        case 36: return pick_regop_n<36>();
+        case 64: return pick_regop_n<64>();
+        default: return nullptr;
+    }
+}
+
 int check_handle(pbte_handle *h)
 {
     if (!h) return fail(PBTE_ERR_INVALID, "null handle");
@@ -349,7 +376,40 @@ int enqueue_sweep(pbte_handle *h, int piv, int64_t *launch_count)
     {
         // one marching CTA per slot, then one streaming pass for the moments
         const DevMarch S = make_dev_march(h);
-        pick_march_kernel(h->n, h->march_stage)<<<h->nslots(), march_threads(h->n), h->march_smem, h->stream>>>(P, S);
+#ifdef PBTE_TRACE
+        if (const char *path = std::getenv("PBTE_TRACE_FILE"))
+        {
+            // development build: per-tile clock stamps of CTA 0 of this sweep, dumped as text (one row per tile)
+            const size_t rows_t = (size_t)h->march_ntiles, cnt = rows_t * 16;
+            if (!h->m_trace.p) CK(h->m_trace.alloc(cnt));
+            CK(cudaMemsetAsync(h->m_trace.p, 0, cnt * sizeof(long long), h->stream));
+            DevMarch St = make_dev_march(h);
+            if (h->march_regop) pick_regop_kernel(h->n)<<<h->nslots(), regop_threads(h->n), h->march_smem, h->stream>>>(P, St);
+            else pick_march_kernel(h->n, h->march_stage)<<<h->nslots(), march_threads(h->n), h->march_smem, h->stream>>>(P, St);
+            std::vector<long long> host(cnt);
+            CK(cudaMemcpyAsync(host.data(), h->m_trace.p, cnt * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            if (FILE *f = std::fopen(path, "w"))
+            {
+                long long t0 = 0;
+                for (size_t i = 0; i < cnt; ++i)
+                    if (host[i] && (!t0 || host[i] < t0)) t0 = host[i];
+                for (size_t r = 0; r < rows_t; ++r)
+                {
+                    bool any = false;
+                    for (int k = 0; k < 16; ++k) any = any || host[r * 16 + k];
+                    if (!any) continue;
+                    std::fprintf(f, "%zu", r);
+                    for (int k = 0; k < 9; ++k) std::fprintf(f, " %lld", host[r * 16 + k] ? host[r * 16 + k] - t0 : -1);
+                    std::fprintf(f, "\n");
+                }
+                std::fclose(f);
+            }
+        }
+        else
+#endif
+        if (h->march_regop) pick_regop_kernel(h->n)<<<h->nslots(), regop_threads(h->n), h->march_smem, h->stream>>>(P, S);
+        else pick_march_kernel(h->n, h->march_stage)<<<h->nslots(), march_threads(h->n), h->march_smem, h->stream>>>(P, S);
         const size_t block = (size_t)h->ne * h->n, count = (size_t)(1 + h->dim) * block;
         const int chunks = h->mom_chunks, per = (h->nslots() + chunks - 1) / chunks;
         moments_from_flux_kernel<<<dim3((unsigned)((block + 255) / 256), (unsigned)chunks), 256, 0, h->stream>>>(P, chunks > 1 ? h->partial.p : h->mom.p, per);
@@ -509,13 +569,38 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
         return false;
     };
     int ring = 0;
-    if (allow_stage && ring_for(sm_half, true, &ring)) h->march_stage = true;
-    else if (allow_stage && ring_for(sm_total - 1024, true, &ring)) h->march_stage = true;
-    else if (ring_for(sm_half, false, &ring) || ring_for(sm_total - 1024, false, &ring)) h->march_stage = false;
-    else return fail(PBTE_ERR_INVALID, "marching kernel does not fit in shared memory for this ndof / level count");
+    // One operator class with at most kRegMaxIn inflow faces: the register-operator kernel (opt-in with PBTE_MARCH_REGOP=1 while it is
+    // slower than the shared-memory operators on C2: profiles/README.md).  Ring: as deep as the CTA's share of shared memory allows, at least two tiles
+    // per consumer group.
+    h->march_regop = false;
+    if (noc == 1 && sched.max_inflow <= kRegMaxIn && pick_regop_kernel(n) != nullptr && (std::getenv("PBTE_MARCH_REGOP") && std::atoi(std::getenv("PBTE_MARCH_REGOP")) != 0))
+    {
+        const size_t budget = regop_ctas(n) == 2 ? sm_half : sm_total - 1024;
+        for (int r = 16; r >= 2 * regop_groups(n) && r >= 4; r -= 2)
+            if (regop_meta_bytes(n, r, h_doubles) + 16 + (size_t)r * slot_bytes <= budget)
+            {
+                h->march_regop = true;
+                ring = r;
+                break;
+            }
+    }
+    MarchKernelFn fn = nullptr;
+    if (h->march_regop)
+    {
+        h->march_stage = false;
+        h->march_smem = regop_meta_bytes(n, ring, h_doubles) + 16 + (size_t)ring * slot_bytes;
+        fn = pick_regop_kernel(n);
+    }
+    else
+    {
+        if (allow_stage && ring_for(sm_half, true, &ring)) h->march_stage = true;
+        else if (allow_stage && ring_for(sm_total - 1024, true, &ring)) h->march_stage = true;
+        else if (ring_for(sm_half, false, &ring) || ring_for(sm_total - 1024, false, &ring)) h->march_stage = false;
+        else return fail(PBTE_ERR_INVALID, "marching kernel does not fit in shared memory for this ndof / level count");
+        h->march_smem = (h->march_stage ? stage_bytes : 0) + 64 + march_meta_bytes(sched.max_levels, noc, ring, sched.max_class_tiles, h_doubles) + (size_t)ring * slot_bytes;
+        fn = pick_march_kernel(n, h->march_stage);
+    }
     h->march_ring = ring;
-    h->march_smem = (h->march_stage ? stage_bytes : 0) + 64 + march_meta_bytes(sched.max_levels, noc, ring, sched.max_class_tiles, h_doubles) + (size_t)ring * slot_bytes;
-    MarchKernelFn fn = pick_march_kernel(n, h->march_stage);
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->march_smem));
 
     const size_t build_smem = 2 * (size_t)n * n * sizeof(double);
@@ -1115,7 +1200,10 @@ int pbte_cuda_sweep(pbte_handle_t *h)
     if (h->pivots.p) piv = h->pivots_recorded ? 2 : 1;
     CK(cudaEventRecord(h->ev0, h->stream));
     int64_t launches = 0;
-    const bool graph_ok = h->use_graph && piv != 1 && h->max_levels > 0;
+    bool graph_ok = h->use_graph && piv != 1 && h->max_levels > 0;
+#ifdef PBTE_TRACE
+    if (std::getenv("PBTE_TRACE_FILE")) graph_ok = false;  // the traced sweep synchronises and writes a file
+#endif
     if (graph_ok)
     {
         if (!h->graph_exec || h->graph_mode != piv)
@@ -1329,6 +1417,7 @@ int pbte_cuda_get_stats(pbte_handle_t *h, pbte_stats_t *s)
     s->n_operator_classes = h->plan.ok ? h->plan.noclass : 0;
     s->march_tiles = h->march_ntiles;
     s->march_fill = h->march_fill;
+    s->march_variant = h->kernel_used == 3 && h->march_regop ? 1 : 0;
     s->operator_bytes = (int64_t)((h->m_ops.count + h->m_oph.count) * sizeof(double));
     return PBTE_OK;
 }

@@ -312,79 +312,91 @@ inline MarchSchedule build_march_schedule(const SharedPlan &plan, int nclass, co
             S.max_inflow = std::max(S.max_inflow, (int)__builtin_popcount(m));
         }
         int nlev = 0;
-        for (int e = 0; e < ne; ++e)
+        for (int e = 0; e < ne; ++e) nlev = std::max(nlev, lv[e] + 1);
+        // elements bucketed by level (ascending id inside a level)
+        std::vector<int32_t> lev_begin(nlev + 1, 0), by_level(ne);
+        for (int e = 0; e < ne; ++e) ++lev_begin[lv[e] + 1];
+        for (int L = 0; L < nlev; ++L) lev_begin[L + 1] += lev_begin[L];
         {
-            nlev = std::max(nlev, lv[e] + 1);
-            keyed[e] = {(int64_t)lv[e] * plan.noclass + plan.elem_oclass[e], e};
+            std::vector<int32_t> cur(lev_begin.begin(), lev_begin.end() - 1);
+            for (int e = 0; e < ne; ++e) by_level[cur[lv[e]]++] = e;
         }
-        std::sort(keyed.begin(), keyed.end());
         S.max_levels = std::max(S.max_levels, nlev);
         S.cls_level_begin[c + 1] = S.cls_level_begin[c] + nlev + 1;
         S.level_tile_begin.resize(S.cls_level_begin[c + 1]);
         int32_t *ltb = S.level_tile_begin.data() + S.cls_level_begin[c];
-        int cur_level = -1;
-        for (int i = 0; i < ne;)
+        const int t_begin = S.ntiles;
+        std::vector<int32_t> tile_of(ne, -1);  // tile (index in class) that holds an element, known for the finished levels
+        for (int L = 0; L < nlev; ++L)
         {
-            const int e0 = keyed[i].second, L = lv[e0], o = plan.elem_oclass[e0];
-            while (cur_level < L) ltb[++cur_level] = S.ntiles;
-            int cnt = 0;
-            const size_t base = S.tile_desc.size();
-            S.tile_desc.resize(base + (size_t)rows * kTileElems, kSrcSkip);
-            S.tile_oclass.push_back(o);
+            ltb[L] = S.ntiles;
+            // Order inside a level: operator class, then the LAST tile any upwind neighbour lies in, then id.  The marching kernel
+            // starts a tile once every tile up to its last prerequisite is stored, so tiles whose prerequisites finish early come
+            // first and the next level overlaps the tail of this one (any order inside a level gives the same numbers: a sweep
+            // depends on the DAG only).
+            const int cnt_l = lev_begin[L + 1] - lev_begin[L];
+            for (int k = 0; k < cnt_l; ++k)
             {
-                int32_t *hdr = S.tile_desc.data() + base + (size_t)(1 + F) * kTileElems;
-                for (int k = 0; k < kTileElems; ++k) hdr[k] = 0;
-                hdr[0] = o;
-                hdr[1] = L;
-                hdr[2] = S.ntiles - ltb[0];
-            }
-            while (i < ne && cnt < kTileElems && keyed[i].first == (int64_t)L * plan.noclass + o)
-            {
-                const int e = keyed[i].second;
-                S.tile_desc[base + cnt] = e;
-                // row 1+m = m-th inflow face of the operator class (ascending canonical face index): the kernel reads the
-                // rows without knowing the class
-                int m = 0;
-                for (unsigned rest = inm[o]; rest; rest &= rest - 1, ++m)
+                const int e = by_level[lev_begin[L] + k];
+                int dep = -1;
+                for (int j = 0; j < F; ++j)
                 {
-                    const int j = __builtin_ctz(rest);
                     const size_t cs = (size_t)e * F + j;
-                    const int f = plan.cface[cs];
-                    int32_t code = kSrcSkip;
-                    if (plan.cnbr[cs] >= 0 && (mi[e] >> f & 1u)) code = plan.cnbr[cs];
-                    else if (plan.cnbr[cs] == PBTE_FACE_BOUNDARY && (mb[e] >> f & 1u)) code = kSrcWall;
-                    S.tile_desc[base + (size_t)(1 + m) * kTileElems + cnt] = code;
+                    if (plan.cnbr[cs] >= 0 && (mi[e] >> plan.cface[cs] & 1u)) dep = std::max(dep, (int)tile_of[plan.cnbr[cs]]);
                 }
-                ++cnt;
-                ++i;
+                keyed[k] = {((int64_t)plan.elem_oclass[e] << 32) | (int64_t)(uint32_t)(dep + 1), e};
             }
-            ++S.ntiles;
-        }
-        while (cur_level < nlev) ltb[++cur_level] = S.ntiles;
-        // last prerequisite tile of every tile of this class
-        {
-            const int t_begin = ltb[0], t_end = S.ntiles;
-            S.max_class_tiles = std::max(S.max_class_tiles, t_end - t_begin);
-            std::vector<int32_t> tile_of(ne, -1);
-            for (int t = t_begin; t < t_end; ++t)
+            std::sort(keyed.begin(), keyed.begin() + cnt_l);
+            for (int i = 0; i < cnt_l;)
+            {
+                const int o = plan.elem_oclass[keyed[i].second];
+                int cnt = 0;
+                const size_t base = S.tile_desc.size();
+                S.tile_desc.resize(base + (size_t)rows * kTileElems, kSrcSkip);
+                S.tile_oclass.push_back(o);
+                {
+                    int32_t *hdr = S.tile_desc.data() + base + (size_t)(1 + F) * kTileElems;
+                    for (int k = 0; k < kTileElems; ++k) hdr[k] = 0;
+                    hdr[0] = o;
+                    hdr[1] = L;
+                    hdr[2] = S.ntiles - t_begin;
+                }
+                int dep = -1;
+                while (i < cnt_l && cnt < kTileElems && plan.elem_oclass[keyed[i].second] == o)
+                {
+                    const int e = keyed[i].second;
+                    S.tile_desc[base + cnt] = e;
+                    // row 1+m = m-th inflow face of the operator class (ascending canonical face index): the kernel reads the
+                    // rows without knowing the class
+                    int m = 0;
+                    for (unsigned rest = inm[o]; rest; rest &= rest - 1, ++m)
+                    {
+                        const int j = __builtin_ctz(rest);
+                        const size_t cs = (size_t)e * F + j;
+                        const int f = plan.cface[cs];
+                        int32_t code = kSrcSkip;
+                        if (plan.cnbr[cs] >= 0 && (mi[e] >> f & 1u)) code = plan.cnbr[cs];
+                        else if (plan.cnbr[cs] == PBTE_FACE_BOUNDARY && (mb[e] >> f & 1u)) code = kSrcWall;
+                        S.tile_desc[base + (size_t)(1 + m) * kTileElems + cnt] = code;
+                        if (code >= 0) dep = std::max(dep, (int)tile_of[code]);
+                    }
+                    ++cnt;
+                    ++i;
+                }
+                // header word 3: last prerequisite tile (index in class; -1 none)
+                S.tile_desc[base + (size_t)(1 + F) * kTileElems + 3] = dep;
+                ++S.ntiles;
+            }
+            // the tiles of this level become visible to the next one
+            for (int t = ltb[L]; t < S.ntiles; ++t)
                 for (int k = 0; k < kTileElems; ++k)
                 {
                     const int e = S.tile_desc[(size_t)t * rows * kTileElems + k];
                     if (e >= 0) tile_of[e] = t - t_begin;
                 }
-            for (int t = t_begin; t < t_end; ++t)
-            {
-                int32_t *d = S.tile_desc.data() + (size_t)t * rows * kTileElems;
-                int dep = -1;
-                for (int m = 0; m < F; ++m)
-                    for (int k = 0; k < kTileElems; ++k)
-                    {
-                        const int code = d[(size_t)(1 + m) * kTileElems + k];
-                        if (code >= 0) dep = std::max(dep, (int)tile_of[code]);
-                    }
-                d[(size_t)(1 + F) * kTileElems + 3] = dep;
-            }
         }
+        ltb[nlev] = S.ntiles;
+        S.max_class_tiles = std::max(S.max_class_tiles, S.ntiles - t_begin);
     }
     S.fill = S.ntiles ? (double)nclass * ne / ((double)kTileElems * S.ntiles) : 0.0;
     return S;

@@ -45,6 +45,7 @@ struct DevMarch
     const int32_t *oc_ksrc, *oc_gsrc; // [noclass][F] element*F + local face, or -1
     const uint8_t *cface;             // [ne][F] canonical -> local face
     const int32_t *cnbr;              // [ne][F] canonical face -> neighbour / PBTE_FACE_BOUNDARY / PBTE_FACE_NONE
+    long long *trace;                 // development builds (-DPBTE_TRACE) only: per-tile clock stamps of CTA 0, else null
 };
 
 // fragment geometry for ndof = N

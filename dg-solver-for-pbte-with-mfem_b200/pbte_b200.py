@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_DIR = os.path.join(PKG_DIR, "lib")
+LIB_DIR = os.environ.get("PBTE_LIB_DIR") or os.path.join(PKG_DIR, "lib")  # PBTE_LIB_DIR: development builds (tools/)
 
 PBTE_OK = 0
 ERR = {-1: "PBTE_ERR_INVALID", -2: "PBTE_ERR_CUDA", -3: "PBTE_ERR_SWEEP_STALL", -4: "PBTE_ERR_MISSING_BC",
@@ -50,7 +50,7 @@ class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("sweeps", C.c_int64), ("last_sweep_ms", C.c_double),
                 ("last_finish_ms", C.c_double), ("flux_bytes", C.c_int64), ("launches_per_sweep", C.c_int64),
                 ("kernel_used", C.c_int32), ("n_classes", C.c_int32), ("max_levels", C.c_int32),
-                ("n_operator_classes", C.c_int32), ("march_tiles", C.c_int32), ("reserved", C.c_int32),
+                ("n_operator_classes", C.c_int32), ("march_tiles", C.c_int32), ("march_variant", C.c_int32),
                 ("march_fill", C.c_double), ("operator_bytes", C.c_int64)]
 
 

@@ -182,7 +182,7 @@ typedef struct pbte_stats
     int32_t max_levels;
     int32_t n_operator_classes; /* element classes with identical local operators (0 = not classified)  */
     int32_t march_tiles;      /* 8-element tiles of the marching schedule (all DAG classes)            */
-    int32_t reserved;
+    int32_t march_variant;    /* marching path: 0 operators in shared memory, 1 operators in registers */
     double march_fill;        /* elements / (8 * tiles): occupancy of the MMA row blocks               */
     int64_t operator_bytes;   /* device bytes of the precomputed shared operators                      */
 } pbte_stats_t;

@@ -4,6 +4,8 @@
 //   2 cp.async 16 B, chunks in memory order over the lanes (coalesced 512 B per instruction)
 //   3 cp.async.bulk (TMA) one 224 B row per lane, completion on an mbarrier
 //   4 ld.global.v2.f64 + st.shared.v2.f64 in memory order (register staged)
+//   5 cp.async 16 B, a lane owns one chunk column, two whole rows per instruction (the pattern of sweep_regop.cuh), zero-fill operand
+//   6 as 5, but issue only: no wait at all inside the loop (cycles a warp needs to get a tile's copies out)
 // Each CTA = W producer warps, each warp gathers its own sequence of tiles (pseudo-random rows of a 0.9 MB region).
 #include <cstdio>
 #include <cstdint>
@@ -63,6 +65,26 @@ __global__ void probe(const unsigned char *g, int nrows_g, int tiles, long long 
             if (depth == 1) asm volatile("cp.async.wait_group 0;" ::: "memory");
             else asm volatile("cp.async.wait_group 1;" ::: "memory");
         }
+        else if (V == 5 || V == 6)
+        {
+            const int r_sub = lane / CH, c = lane - r_sub * CH;
+            const unsigned char *cb = base + c * 16;
+            const uint32_t d0 = s32(dst) + r_sub * ROWB + c * 16;
+#pragma unroll
+            for (int k = 0; k < NROW / 2; ++k)
+            {
+                const int row = 2 * k + r_sub;
+                const int rr = __shfl_sync(0xffffffffu, row < 32 ? r0 : r1, row & 31);
+                if (r_sub < 2)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d0 + k * 2 * ROWB), "l"(cb + (size_t)rr * ROWB), "r"(rr >= 0 ? 16u : 0u) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (V == 5)
+            {
+                if (depth == 1) asm volatile("cp.async.wait_group 0;" ::: "memory");
+                else asm volatile("cp.async.wait_group 1;" ::: "memory");
+            }
+        }
         else if (V == 3)
         {
             uint64_t *b = bar + (t % depth);
@@ -101,7 +123,7 @@ __global__ void probe(const unsigned char *g, int nrows_g, int tiles, long long 
                 if (idx < NROW * CH) *reinterpret_cast<double2 *>(dst + idx * 16) = v[k];
             }
         }
-        if (V != 3) acc += reinterpret_cast<const double *>(dst)[lane];
+        if (V != 3 && V != 6) acc += reinterpret_cast<const double *>(dst)[lane];
     }
     if (V == 3)
         for (int d = 0; d < depth && d < tiles; ++d)
@@ -145,13 +167,15 @@ int main()
     cudaMalloc(&cyc, 8);
     cudaMalloc(&sink, 296 * 256 * 8);
     for (int ctas : {148, 296})
-        for (int warps : {1, 2, 4})
+        for (int warps : {1, 2, 4, 8})
             for (int depth : {1, 2})
             {
                 run<1>(g, nrows_g, warps, depth, ctas, cyc, sink);
                 run<2>(g, nrows_g, warps, depth, ctas, cyc, sink);
                 run<3>(g, nrows_g, warps, depth, ctas, cyc, sink);
                 if (depth == 1) run<4>(g, nrows_g, warps, depth, ctas, cyc, sink);
+                run<5>(g, nrows_g, warps, depth, ctas, cyc, sink);
+                if (depth == 2) run<6>(g, nrows_g, warps, depth, ctas, cyc, sink);
             }
     return 0;
 }
