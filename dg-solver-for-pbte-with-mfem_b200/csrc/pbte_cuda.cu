@@ -400,7 +400,7 @@ int enqueue_sweep(pbte_handle *h, int piv, int64_t *launch_count)
                     for (int k = 0; k < 16; ++k) any = any || host[r * 16 + k];
                     if (!any) continue;
                     std::fprintf(f, "%zu", r);
-                    for (int k = 0; k < 9; ++k) std::fprintf(f, " %lld", host[r * 16 + k] ? host[r * 16 + k] - t0 : -1);
+                    for (int k = 0; k < 11; ++k) std::fprintf(f, " %lld", host[r * 16 + k] ? host[r * 16 + k] - t0 : -1);
                     std::fprintf(f, "\n");
                 }
                 std::fclose(f);
@@ -559,8 +559,9 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
     auto ring_for = [&](size_t budget, bool stage, int *ring) {
         const size_t fixed = (stage ? stage_bytes : 0) + 64;
         // mbarrier parity waits are only valid within one phase of the barrier: a slot is always refilled by the same producer
-        // warp (ring size a multiple of the producer warps per role) and the ring holds at least one tile per consumer warp
-        for (int r = 16; r >= march_consumers(n); r -= 2)
+        // warp (ring size a multiple of the producer warps per role) and the ring holds at least one tile per consumer warp (a
+        // consumer must find the slot of its next tile at most one phase behind)
+        for (int r = 16; r >= march_min_ring(n); r -= 2)
             if (fixed + march_meta_bytes(sched.max_levels, noc, r, sched.max_class_tiles, h_doubles) + (size_t)r * slot_bytes <= budget)
             {
                 *ring = r;
@@ -569,20 +570,27 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
         return false;
     };
     int ring = 0;
-    // One operator class with at most kRegMaxIn inflow faces: the register-operator kernel (opt-in with PBTE_MARCH_REGOP=1 while it is
-    // slower than the shared-memory operators on C2: profiles/README.md).  Ring: as deep as the CTA's share of shared memory allows, at least two tiles
-    // per consumer group.
+    // One operator class with at most kRegMaxIn inflow faces can use the register-operator kernel (sweep_regop.cuh).  Measured
+    // (profiles/README.md): it wins where a slot's operators do not fit the half-SM share of shared memory (hex order 3: 131 KB,
+    // 0.28 against 0.37 ms on 512 hexes x 256 slots) and loses ~10 % where they do (hex order 2, quad order 4), so that is the
+    // automatic rule; PBTE_MARCH_REGOP=0/1 forces a variant.  Ring: as deep as the CTA's share of shared memory allows, at least
+    // two tiles per consumer group.
     h->march_regop = false;
-    if (noc == 1 && sched.max_inflow <= kRegMaxIn && pick_regop_kernel(n) != nullptr && (std::getenv("PBTE_MARCH_REGOP") && std::atoi(std::getenv("PBTE_MARCH_REGOP")) != 0))
     {
-        const size_t budget = regop_ctas(n) == 2 ? sm_half : sm_total - 1024;
-        for (int r = 16; r >= 2 * regop_groups(n) && r >= 4; r -= 2)
-            if (regop_meta_bytes(n, r, h_doubles) + 16 + (size_t)r * slot_bytes <= budget)
-            {
-                h->march_regop = true;
-                ring = r;
-                break;
-            }
+        int unused = 0;
+        bool want = !(allow_stage && ring_for(sm_half, true, &unused));
+        if (const char *ev = std::getenv("PBTE_MARCH_REGOP")) want = std::atoi(ev) != 0;
+        if (want && noc == 1 && sched.max_inflow <= kRegMaxIn && pick_regop_kernel(n) != nullptr)
+        {
+            const size_t budget = regop_ctas(n) == 2 ? sm_half : sm_total - 1024;
+            for (int r = 16; r >= 2 * regop_groups(n) && r >= 4; r -= 2)
+                if (regop_meta_bytes(n, r, h_doubles) + 16 + (size_t)r * slot_bytes <= budget)
+                {
+                    h->march_regop = true;
+                    ring = r;
+                    break;
+                }
+        }
     }
     MarchKernelFn fn = nullptr;
     if (h->march_regop)

@@ -10,9 +10,8 @@
 // pays once per level (46 levels x ~6000 cycles were a quarter of the C2 sweep, profiles/README.md); shared memory only
 // carries the element data (A fragments), and nothing is staged per CTA any more, so the ring is deeper.
 //
-// CTA = one slot.  Warps 0-7 (two warpgroups, registers released with setmaxnreg): 4 source producers + 4 upwind-neighbour
-// producers with the roles of sweep_march_kernel (a warp keeps only ~16 asynchronous copies in flight, so the gather
-// bandwidth of a CTA scales with its producer warps: profiles/README.md).  Then G groups of MT consumer warps; group g takes tiles g, g + G, ...
+// CTA = one slot.  Warps 0-3 (one warpgroup, registers released with setmaxnreg): 2 source producers + 2 upwind-neighbour
+// producers with the roles of sweep_march_kernel.  Then G groups of MT consumer warps; group g takes tiles g, g + G, ...
 // Finished tiles are published per consumer warp as a monotone counter (no atomics); the neighbour producers wait until every
 // warp of every group has passed the tile's last prerequisite (descriptor header word 3).
 #pragma once
@@ -22,7 +21,7 @@
 namespace pbte_dev
 {
 constexpr int kRegMaxIn = 3;  // inflow faces of a Cartesian element: dim
-constexpr int kRegProducerWarps = 8;  // two warpgroups: 4 source + 4 upwind-neighbour loaders (tile p, p + 4, ... each)
+constexpr int kRegProducerWarps = 4;  // one warpgroup: 2 source + 2 upwind-neighbour loaders (tile p, p + 2, ... each); 4 + 4 measured no faster
 constexpr int kRegRoleWarps = kRegProducerWarps / 2;
 
 // groups per CTA: eight consumer warps where the column blocks allow it
@@ -35,10 +34,10 @@ __host__ __device__ constexpr int regop_consumer_warps(int n) { return ((regop_g
 __host__ __device__ constexpr int regop_threads(int n) { return (kRegProducerWarps + regop_consumer_warps(n)) * 32; }
 // CTAs per SM the register file allows: (1 + nin) * KS operator doubles per consumer lane
 __host__ __device__ constexpr int regop_ctas(int n) { return n <= 32 ? 2 : 1; }
-__host__ __device__ constexpr int regop_consumer_regs(int n) { return n <= 32 ? 96 : 216; }
+__host__ __device__ constexpr int regop_consumer_regs(int n) { return n <= 32 ? 104 : 232; }
 __host__ __device__ constexpr int regop_producer_regs(int n) { return n <= 32 ? 32 : 40; }
 // register pool of a CTA: (launch registers) * threads >= producers * producer_regs + consumers * consumer_regs
-//   n <= 32: 512 threads, 2 CTAs/SM -> 64 at launch: 256 * 32 + 256 * 96 = 32768;  n > 32: 512 threads, 1 CTA/SM -> 128: 256 * 40 + 256 * 216 = 65536
+//   n <= 32: 384 threads, 2 CTAs/SM -> 80 at launch: 128 * 32 + 256 * 104 = 30720;  n > 32: 384 threads, 1 CTA/SM -> 168: 128 * 40 + 256 * 232 = 64512
 __host__ __device__ constexpr bool regop_supported(int n) { return n >= 4 && n <= 64; }
 
 __host__ __device__ inline size_t regop_meta_bytes(int n, int ring, size_t h_doubles)
@@ -68,22 +67,6 @@ __device__ __forceinline__ int ld_acquire_shared(const int32_t *p)
     asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
     return v;
 }
-// Development aid (-DPBTE_TRACE, never in the shipped library): CTA 0 records clock64 stamps per tile, 16 columns per tile:
-// consumer (column block 0 of the group) 0 wait start, 1 full, 2 MMAs done, 3 stored; neighbour producer 4 slot free, 5 prerequisites
-// stored, 6 copies issued; source producer 7 slot free, 8 copies issued.
-#ifdef PBTE_TRACE
-#define PBTE_STAMP(tile, col)                                                                              \
-    do                                                                                                     \
-    {                                                                                                      \
-        if (S.trace && blockIdx.x == 0 && lane == 0) S.trace[(size_t)(tile) * 16 + (col)] = clock64();     \
-    } while (0)
-#else
-#define PBTE_STAMP(tile, col) \
-    do                        \
-    {                         \
-    } while (0)
-#endif
-
 // grid = nslots CTAs of regop_threads(N) threads.  Dynamic shared memory = [progress counters | barriers | wall vectors | tile ring].
 template <int N>
 __global__ void __launch_bounds__(regop_threads(N), regop_ctas(N)) sweep_march_regop_kernel(DevProblem P, DevMarch S)

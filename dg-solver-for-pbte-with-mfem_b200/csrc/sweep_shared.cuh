@@ -17,6 +17,8 @@
 
 #include "common.cuh"
 
+#include <type_traits>
+
 namespace pbte_dev
 {
 constexpr int kTile = 8;             // elements per tile (must equal pbte_host::kTileElems)
@@ -312,6 +314,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
             : "memory");
     }
 }
+// one non-blocking probe of a barrier phase
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // 16-byte asynchronous copy global -> shared through L2 (src_bytes = 0 writes zeros)
 __device__ __forceinline__ void cp_async16(void *dst, const void *src, uint32_t src_bytes)
 {
@@ -323,10 +340,38 @@ __device__ __forceinline__ void cp_async_arrive(uint64_t *bar)
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// Development aid (-DPBTE_TRACE, never in the shipped library): CTA 0 records clock64 stamps per tile, 16 columns per tile:
+// consumer 0 wait start, 1 full, 9 descriptor read, 2 MMAs done, 10 stored, 3 published; neighbour producer 4 slot free, 5 prerequisites
+// stored, 6 copies issued; source producer 7 slot free, 8 copies issued.
+#ifdef PBTE_TRACE
+#define PBTE_STAMP(tile, col)                                                                              \
+    do                                                                                                     \
+    {                                                                                                      \
+        if (S.trace && blockIdx.x == 0 && lane == 0) S.trace[(size_t)(tile) * 16 + (col)] = clock64();     \
+    } while (0)
+#else
+#define PBTE_STAMP(tile, col) \
+    do                        \
+    {                         \
+    } while (0)
+#endif
+
 constexpr int kMaxIn = 4;          // inflow faces whose wall temperature a consumer lane prefetches (tri 2, quad/hex dim, tet 3)
 // MMA (consumer) warps of a marching CTA: two per SM sub-partition, so that one covers the other's descriptor / wall / store
 // phases; one per sub-partition for large elements (registers, and the ring must hold at least one tile per consumer)
-__host__ __device__ constexpr int march_consumers(int n) { return n <= 36 ? 8 : 4; }
+// Tile pairs (compile-time experiment, off): a consumer warp takes two consecutive tiles per pass where the second does not depend
+// on the first, so every operator fragment read from shared memory feeds two MMAs; four consumer warps per CTA then, each holding two
+// ring slots.  Measured on C2 (profiles/README.md): 97 % of the tiles pair up, the sweep takes 0.51 ms against 0.45 ms with eight
+// single-tile consumers: shared-memory traffic is not what bounds the kernel, the number of warps covering each other's non-MMA
+// phases is.
+#ifndef PBTE_PAIR_TILES
+#define PBTE_PAIR_TILES 0
+#endif
+__host__ __device__ constexpr bool march_pair_tiles(int n) { return PBTE_PAIR_TILES != 0 && n <= 36; }
+__host__ __device__ constexpr int march_consumers(int n) { return n <= 36 ? (march_pair_tiles(n) ? 4 : 8) : 4; }
+// ring slots a CTA needs at least: one per tile a consumer warp can hold (an mbarrier parity wait is only meaningful within one
+// phase of its barrier: a consumer must find the slot of its next tile at most one phase behind)
+__host__ __device__ constexpr int march_min_ring(int n) { return march_consumers(n) * (march_pair_tiles(n) ? 2 : 1); }
 constexpr int kSrcWarps = 2;       // source loaders (run ahead of the wavefront); warp p takes tiles p, p + kSrcWarps, ...
 constexpr int kNbrWarps = 2;       // upwind-neighbour loaders (follow the wavefront), same interleaving
 static_assert(kSrcWarps == 2 && kNbrWarps == 2, "ring sizes are chosen even so that every slot has one producer warp per role");
@@ -363,13 +408,14 @@ __host__ __device__ inline size_t march_meta_bytes(int max_levels, int noclass, 
 //                     consumers set a bit per finished tile, the producer advances a watermark over the bitmap (no level-wide
 //                     barrier: tiles of the next level start as soon as their own upwind tiles are done); cp.async of the
 //                     upwind neighbour rows (L2 hits: written by this CTA a level ago).  Both producers complete full[slot].
-//   consumer w        tiles i = w mod 4: waits full[slot]; U = X P^T + sum_m Unbr_m Q_m^T by mma.sync m8n8k4 FP64 with A
+//   consumer w        tiles w, w + consumers, ...: waits full[slot]; U = X P^T + sum_m Unbr_m Q_m^T by mma.sync m8n8k4 FP64 with A
 //                     fragments from the ring and B fragments from the staged operators; releases empty[slot]; adds wall
 //                     terms, stores the tile, sets its bit in the bitmap (release).
 template <int N, bool STAGE>
 __global__ void __launch_bounds__(march_threads(N), N <= 36 ? 2 : 1) sweep_march_kernel(DevProblem P, DevMarch S)
 {
     constexpr int kConsumerWarps = march_consumers(N);
+    constexpr bool kPairTiles = march_pair_tiles(N);
     using G = Frag<N>;
     constexpr int MT = G::MT, MP = G::MP, KS = G::KS, FR = G::FR;
     constexpr int NP = (N + 1) & ~1;        // global row stride (doubles): 16-byte aligned rows
@@ -427,29 +473,22 @@ __global__ void __launch_bounds__(march_threads(N), N <= 36 ? 2 : 1) sweep_march
     const int tbase = ltb[0], NT = ltb[nlev] - tbase;
     double *u = P.flux + (size_t)s * P.ne * NP;
 
-    // Copy patterns of the producers.  A tile needs 16 source rows (u_old and T_old of its 8 elements) and 8 rows per inflow
-    // face, NP doubles each.  The 16-byte chunks are dealt to the lanes in memory order (chunk k*32 + lane), so one cp.async
-    // instruction covers whole contiguous rows: full 32-byte sectors and few distinct cache lines per instruction (a row per
-    // lane would be bound by the one-line-per-cycle tag stage of L1TEX: 16 B/clk/SM measured, tools/copy_probe.cu).  The
-    // (row, chunk) of every (k, lane) is fixed, so it is packed once: bits 0-4 row, bits 5-9 chunk, bits 16-31 byte offset
-    // of the chunk inside the staged vectors.
-    auto pack_pattern = [&](int idx, int nrows) -> int {
-        const int row = idx / CH, ch = idx - row * CH;
-        return idx < nrows * CH ? (row | (ch << 5) | ((row * NS * 8 + ch * 16) << 16)) : -1;
-    };
+    // Copy pattern of the producers.  A tile needs 16 source rows (u_old and T_old of its 8 elements) and 8 rows per inflow
+    // face, NP doubles each.  A lane owns one 16-byte chunk column and an instruction covers RPI = 32 / CH whole rows: rows are
+    // contiguous, so one cp.async instruction still touches full 32-byte sectors and few cache lines (a row per lane would be
+    // bound by the one-line-per-cycle tag stage of L1TEX: 16 B/clk/SM measured, tools/copy_probe.cu), and per instruction a
+    // lane needs just one shuffle (the row's element) and one multiply-add (the address): the shared-memory offset is a
+    // per-lane constant plus an immediate.
+    constexpr int RPI = 32 / CH;
+    static_assert(RPI >= 1, "a row is at most 32 chunks of 16 bytes");
+    const int r_sub = lane / CH, lch = lane - r_sub * CH;
+    const bool lane_copies = r_sub < RPI;
+    const uint32_t lane_off = (uint32_t)(r_sub * NS * 8 + lch * 16);  // offset of the lane's chunk inside the staged vectors
     if (warp >= kConsumerWarps && warp < kConsumerWarps + kSrcWarps)
     {
         // ---- source producer ------------------------------------------------------------------------------------
-        constexpr int IT = (16 * CH + 31) / 32;
-        int pat[IT];
-        const unsigned char *pbase[IT];  // base pointer (u or T_old) + chunk offset of (k, lane)
-#pragma unroll
-        for (int k = 0; k < IT; ++k)
-        {
-            pat[k] = pack_pattern(k * 32 + lane, 16);
-            const int row = pat[k] & 31, ch = (pat[k] >> 5) & 31;
-            pbase[k] = reinterpret_cast<const unsigned char *>(row < 8 ? u : P.tc_prev) + ch * 16;
-        }
+        constexpr int ITS = (16 + RPI - 1) / RPI;
+        const unsigned char *ub = reinterpret_cast<const unsigned char *>(u) + lch * 16, *tb = reinterpret_cast<const unsigned char *>(P.tc_prev) + lch * 16;
         const int q = lane & 7;  // lanes 0-7 hold the elements of the u_old rows, lanes 8-15 the same elements for the T_old rows
         const int first = warp - kConsumerWarps;
         int e_next = first < NT ? __ldg(S.tile_desc + (size_t)(tbase + first) * rows * kTile + q) : -1;
@@ -461,16 +500,17 @@ __global__ void __launch_bounds__(march_threads(N), N <= 36 ? 2 : 1) sweep_march
             if (i + kSrcWarps < NT) e_next = __ldg(desc_g + (size_t)kSrcWarps * rows * kTile + q);
             if (it > 0) mbar_wait(empty + slot, (it - 1) & 1);
             unsigned char *sl = ring + (size_t)slot * slot_bytes;
-            const uint32_t vb = smem_u32(sl + hdr_bytes);
+            PBTE_STAMP(i, 7);
+            const uint32_t vb = smem_u32(sl + hdr_bytes) + lane_off;
 #pragma unroll
-            for (int k = 0; k < IT; ++k)
+            for (int k = 0; k < ITS; ++k)
             {
-                const int er = __shfl_sync(0xffffffffu, e, pat[k] & 15);
-                if (pat[k] >= 0)
+                const int row = k * RPI + r_sub;  // rows 0-7 u_old, 8-15 T_old of the tile's elements
+                const int er = __shfl_sync(0xffffffffu, e, row & 7);
+                if (lane_copies && row < 16)
                 {
-                    const unsigned char *src = pbase[k] + (size_t)(er < 0 ? 0 : er) * (NP * 8);
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vb + ((unsigned)pat[k] >> 16)), "l"(src), "r"(er >= 0 ? 16u : 0u)
-                                 : "memory");
+                    const unsigned char *src = (row < 8 ? ub : tb) + (size_t)(er < 0 ? 0 : er) * (NP * 8);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vb + (uint32_t)(k * RPI * NS * 8)), "l"(src), "r"(er >= 0 ? 16u : 0u) : "memory");
                 }
             }
             if (lane < rows * 2) cp_async16(sl + lane * 16, reinterpret_cast<const unsigned char *>(desc_g) + lane * 16, 16u);
@@ -482,16 +522,14 @@ __global__ void __launch_bounds__(march_threads(N), N <= 36 ? 2 : 1) sweep_march
                     cp_async16(sl + rows * 32 + lane * 16, S.ctbc + (size_t)(er < 0 ? 0 : er) * Fp + 2 * ch, er >= 0 ? 16u : 0u);
             }
             cp_async_arrive(full + slot);
+            PBTE_STAMP(i, 8);
         }
     }
     else if (warp >= kConsumerWarps + kSrcWarps)
     {
         // ---- upwind-neighbour producer --------------------------------------------------------------------------
-        constexpr int IT = CH;  // up to 4 inflow faces (32 rows) per pass: 32*CH chunks
-        int pat[IT];
-#pragma unroll
-        for (int k = 0; k < IT; ++k) pat[k] = pack_pattern(k * 32 + lane, 32);
-        const unsigned char *ub = reinterpret_cast<const unsigned char *>(u);
+        constexpr int ITN = (32 + RPI - 1) / RPI;  // up to 4 inflow faces (32 rows) per pass
+        const unsigned char *ub = reinterpret_cast<const unsigned char *>(u) + lch * 16;
         const int q = lane & 7, mq = lane >> 3;
         int wm = 0;  // watermark: tiles [0, wm) of this class are known to be stored
         const int first = warp - kConsumerWarps - kSrcWarps;
@@ -511,7 +549,11 @@ __global__ void __launch_bounds__(march_threads(N), N <= 36 ? 2 : 1) sweep_march
                 code_next = __ldg(dn + (1 + mq) * kTile + q);
             }
             if (it > 0) mbar_wait(empty + slot, (it - 1) & 1);
+            PBTE_STAMP(i, 4);
             // every tile up to the last prerequisite must be stored: advance the watermark over the bitmap of finished tiles
+#ifdef PBTE_NODEP  // timing experiment only (wrong results): how fast is the pipeline when no tile waits for another?
+            wm = dep + 1;
+#endif
             while (wm <= dep)
             {
                 const unsigned w = *reinterpret_cast<volatile unsigned *>(s_done + (wm >> 5)) >> (wm & 31);
@@ -520,6 +562,7 @@ __global__ void __launch_bounds__(march_threads(N), N <= 36 ? 2 : 1) sweep_march
                 else wm += min(ones, 32 - (wm & 31));
             }
             __threadfence_block();  // acquire: the stores of those tiles are visible to the copies issued below
+            PBTE_STAMP(i, 5);
             const int nin = __popc((unsigned)s_inm[o]);
             unsigned char *sl = ring + (size_t)slot * slot_bytes;
             for (int m0 = 0; m0 < nin; m0 += 4)
@@ -527,20 +570,22 @@ __global__ void __launch_bounds__(march_threads(N), N <= 36 ? 2 : 1) sweep_march
                 // lane (mq, q) holds the source code of row mq*8 + q of this pass
                 const int code = m0 == 0 ? code0 : ((m0 + mq < nin) ? __ldg(desc_g + (1 + m0 + mq) * kTile + q) : kSrcSkipCode);
                 const int nrow = min(nin - m0, 4) * kTile;
-                const uint32_t vb = smem_u32(sl + hdr_bytes) + (uint32_t)((2 + m0) * kTile * NS * 8);
+                const uint32_t vb = smem_u32(sl + hdr_bytes) + (uint32_t)((2 + m0) * kTile * NS * 8) + lane_off;
 #pragma unroll
-                for (int k = 0; k < IT; ++k)
+                for (int k = 0; k < ITN; ++k)
                 {
-                    const int cr = __shfl_sync(0xffffffffu, code, pat[k] & 31);
-                    if (pat[k] >= 0 && (pat[k] & 31) < nrow)
+                    if (k * RPI >= nrow) break;
+                    const int row = k * RPI + r_sub;  // lane `row` holds the source of row `row` (face m0 + row / 8, element row % 8)
+                    const int cr = __shfl_sync(0xffffffffu, code, row & 31);
+                    if (lane_copies && row < nrow)
                     {
-                        const unsigned char *src = ub + (size_t)(cr < 0 ? 0 : cr) * (NP * 8) + ((pat[k] >> 5) & 31) * 16;
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vb + ((unsigned)pat[k] >> 16)), "l"(src), "r"(cr >= 0 ? 16u : 0u)
-                                     : "memory");
+                        const unsigned char *src = ub + (size_t)(cr < 0 ? 0 : cr) * (NP * 8);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vb + (uint32_t)(k * RPI * NS * 8)), "l"(src), "r"(cr >= 0 ? 16u : 0u) : "memory");
                     }
                 }
             }
             cp_async_arrive(full + slot);
+            PBTE_STAMP(i, 6);
         }
     }
     else
@@ -549,98 +594,180 @@ __global__ void __launch_bounds__(march_threads(N), N <= 36 ? 2 : 1) sweep_march
         const int q = lane >> 2, r = lane & 3;
         const double c1 = P.slot_c1[s], c2 = P.slot_c2[s];
         const double *oph = S.h_smem ? s_h : S.oph + (size_t)s * noc * F * N;
-        for (int i = warp; i < NT; i += kConsumerWarps)
-        {
-            const int slot = i % R, it = i / R;
-            const unsigned char *sl = ring + (size_t)slot * slot_bytes;
-            const int32_t *sd = reinterpret_cast<const int32_t *>(sl);
-            const double *vec = reinterpret_cast<const double *>(sl + hdr_bytes) + (size_t)q * NS + r;
-            mbar_wait(full + slot, it & 1);
-            const int e = sd[q], o = sd[(1 + F) * kTile];
+        // One pass = T tiles (1 or 2) of one operator class whose ring slots are full: U_t = X_t P^T + sum_m Unbr_t,m Q_m^T.
+        // One matrix block = KS k steps; per k step the B fragments of all MT row blocks (two per 16-byte load from the staged
+        // operator) feed T * MT MMAs, the A fragments come from the staged vectors.  With T = 2 every operator fragment read from
+        // shared memory is used twice: the B fragments are 57 of the 75 KB a tile moves through the shared-memory pipe, and that
+        // pipe, not the FP64 tensor pipe, bounds the kernel (profiles/README.md).  The fragments of KC k steps are loaded
+        // together into their own registers and only then multiplied: no register is rewritten while MMAs that read it are in
+        // flight and every MMA finds its operands ready (interleaved load/MMA code ran at the MMA latency: tools/dmma_probe.cu).
+        auto pass = [&](auto tc, int i0) {
+            constexpr int T = decltype(tc)::value;
+            constexpr int KC0 = (16 / (2 * MP)) < 1 ? 1 : (16 / (2 * MP) > KS ? KS : 16 / (2 * MP));
+            constexpr int KC = KC0 / T < 1 ? 1 : KC0 / T;
+            const unsigned char *sl[T];
+            const int32_t *sd[T];
+            const double *vec[T];
+            int e[T];
+            unsigned wall[T];
+#pragma unroll
+            for (int t = 0; t < T; ++t)
+            {
+                sl[t] = ring + (size_t)((i0 + t) % R) * slot_bytes;
+                sd[t] = reinterpret_cast<const int32_t *>(sl[t]);
+                vec[t] = reinterpret_cast<const double *>(sl[t] + hdr_bytes) + (size_t)q * NS + r;
+                e[t] = sd[t][q];
+                wall[t] = 0;
+            }
+            const int o = sd[0][(1 + F) * kTile];
             const unsigned inm = (unsigned)s_inm[o];
             const int nin = __popc(inm);
             const double *op = ops + (size_t)s_opoff[o] * FR;
-            // source codes of the first kMaxIn inflow faces (rows 1..4 of the descriptor always exist): wall faces of this lane
-            unsigned wall = 0;
+            // what the descriptors say about the inflow faces: the wall faces of this lane's elements, and the faces where some
+            // element of the pass has an interior upwind neighbour
+            unsigned interior = 0;
+            for (int m = 0; m < nin; ++m)
 #pragma unroll
-            for (int m = 0; m < kMaxIn; ++m) wall |= (unsigned)(sd[(1 + m) * kTile + q] == kSrcWallCode && m < nin) << m;
-            const double *tbq = reinterpret_cast<const double *>(sl + rows * 32) + (size_t)q * Fp;  // wall temperatures of element q
-            double acc[MT][2];
+                for (int t = 0; t < T; ++t)
+                {
+                    const int code = sd[t][(1 + m) * kTile + q];
+                    wall[t] |= (unsigned)(code == kSrcWallCode) << m;
+                    interior |= (unsigned)(__ballot_sync(0xffffffffu, code >= 0) != 0u) << m;
+                }
+            double acc[T][MT][2];
 #pragma unroll
-            for (int I = 0; I < MT; ++I) acc[I][0] = acc[I][1] = 0.0;
-            // One matrix block = KS k steps of MT MMAs: A fragment from the staged vector, B fragments (two row blocks per 16-byte
-            // load) from the staged operator.  The fragments of KC k steps are loaded together into their own registers and
-            // only then multiplied: no register is rewritten while MMAs that read it are in flight and every MMA finds its
-            // operands ready, so a warp that is alone on its sub-partition issues at the pipe rate (interleaved load/MMA code
-            // ran at the MMA latency, 26 cycles per MMA instead of 16: tools/dmma_probe.cu, per-tile timeline in profiles/).
-            constexpr int KC = (16 / (2 * MP)) < 1 ? 1 : (16 / (2 * MP) > KS ? KS : 16 / (2 * MP));
-            auto block = [&](const double *va, const double *vt, const double *opb) {
+            for (int t = 0; t < T; ++t)
+#pragma unroll
+                for (int I = 0; I < MT; ++I) acc[t][I][0] = acc[t][I][1] = 0.0;
+            auto block = [&](size_t voff, bool source, const double *opb) {
                 const double2 *bp = reinterpret_cast<const double2 *>(opb) + lane;
 #pragma unroll
                 for (int k0 = 0; k0 < KS; k0 += KC)
                 {
                     double2 bq[KC][MP];
-                    double xa[KC];
+                    double xa[T][KC];
 #pragma unroll
                     for (int k = 0; k < KC; ++k)
                         if (k0 + k < KS)
                         {
 #pragma unroll
                             for (int Ip = 0; Ip < MP; ++Ip) bq[k][Ip] = STAGE ? bp[(Ip * KS + k0 + k) * 32] : __ldg(bp + (Ip * KS + k0 + k) * 32);
-                            xa[k] = vt ? fma(c2, va[4 * (k0 + k)], c1 * vt[4 * (k0 + k)]) : va[4 * (k0 + k)];
+#pragma unroll
+                            for (int t = 0; t < T; ++t)
+                            {
+                                const double *va = vec[t] + voff;
+                                xa[t][k] = source ? fma(c2, va[4 * (k0 + k)], c1 * va[(size_t)kTile * NS + 4 * (k0 + k)]) : va[4 * (k0 + k)];
+                            }
                         }
 #pragma unroll
                     for (int k = 0; k < KC; ++k)
                         if (k0 + k < KS)
                         {
 #pragma unroll
-                            for (int I = 0; I < MT; ++I) dmma_m8n8k4(acc[I][0], acc[I][1], xa[k], (I & 1) ? bq[k][I >> 1].y : bq[k][I >> 1].x);
+                            for (int I = 0; I < MT; ++I)
+#pragma unroll
+                                for (int t = 0; t < T; ++t) dmma_m8n8k4(acc[t][I][0], acc[t][I][1], xa[t][k], (I & 1) ? bq[k][I >> 1].y : bq[k][I >> 1].x);
                         }
                 }
             };
-            block(vec, vec + (size_t)kTile * NS, op);  // source / pseudo-time term: X = c1 T_old + c2 u_old
+            PBTE_STAMP(i0, 9);
+            block(0, true, op);  // source / pseudo-time term: X = c1 T_old + c2 u_old (vectors 0 and 1 of the slot)
             for (int m = 0; m < nin; ++m)
+                if (interior >> m & 1u) block((size_t)(2 + m) * kTile * NS, false, op + (size_t)(1 + m) * FR);
+#ifdef PBTE_TRACE
+            if (acc[0][0][0] == 1.2345e300) PBTE_STAMP(i0, 15);  // the stamp below waits for the accumulators
+#endif
+            PBTE_STAMP(i0, 2);
+#pragma unroll
+            for (int t = 0; t < T; ++t)
             {
-                const int code = sd[(1 + m) * kTile + q];
-                if (m >= kMaxIn && code == kSrcWallCode) wall |= 1u << m;
-                if (__ballot_sync(0xffffffffu, code >= 0) == 0u) continue;  // no lane has an interior upwind neighbour on this face
-                block(vec + (size_t)(2 + m) * kTile * NS, nullptr, op + (size_t)(1 + m) * FR);
+                // isothermal walls on inflow faces: + T_bc h_j   (this lane owns element q, dofs 8I + 2r + {0,1})
+                if (wall[t])
+                {
+                    const double *tbq = reinterpret_cast<const double *>(sl[t] + rows * 32) + (size_t)q * Fp;  // wall temperatures of element q
+                    unsigned rest = inm;
+                    for (int m = 0; rest; ++m, rest &= rest - 1)
+                        if (wall[t] >> m & 1u)
+                        {
+                            const int j = __ffs(rest) - 1;
+                            const double tw = tbq[j];
+                            const double *hj = oph + ((size_t)o * F + j) * N;
+#pragma unroll
+                            for (int I = 0; I < MT; ++I)
+                            {
+                                const int d0 = 8 * I + 2 * r;
+                                if (d0 < N) acc[t][I][0] = fma(tw, hj[d0], acc[t][I][0]);
+                                if (d0 + 1 < N) acc[t][I][1] = fma(tw, hj[d0 + 1], acc[t][I][1]);
+                            }
+                        }
+                }
             }
-            // isothermal walls on inflow faces: + T_bc h_j   (this lane owns element q, dofs 8I + 2r + {0,1})
-            if (wall)
-            {
-                auto add_wall = [&](int j, double t) {
-                    const double *hj = oph + ((size_t)o * F + j) * N;
+            __syncwarp();
+            if (lane == 0)
+#pragma unroll
+                for (int t = 0; t < T; ++t) mbar_arrive(empty + (i0 + t) % R);  // every staged value of the tile has been consumed
+#pragma unroll
+            for (int t = 0; t < T; ++t)
+                if (e[t] >= 0)
+                {
+                    double *dst = u + (size_t)e[t] * NP;
 #pragma unroll
                     for (int I = 0; I < MT; ++I)
                     {
                         const int d0 = 8 * I + 2 * r;
-                        if (d0 < N) acc[I][0] = fma(t, hj[d0], acc[I][0]);
-                        if (d0 + 1 < N) acc[I][1] = fma(t, hj[d0 + 1], acc[I][1]);
+                        if (d0 < N) dst[d0] = acc[t][I][0];
+                        if (d0 + 1 < N) dst[d0 + 1] = acc[t][I][1];
                     }
-                };
-                unsigned rest = inm;
-                for (int m = 0; rest; ++m, rest &= rest - 1)
-                    if (wall >> m & 1u) add_wall(__ffs(rest) - 1, tbq[__ffs(rest) - 1]);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + slot);  // every staged value of the tile (vectors, wall temperatures) has been consumed
-            if (e >= 0)
-            {
-                double *dst = u + (size_t)e * NP;
-#pragma unroll
-                for (int I = 0; I < MT; ++I)
-                {
-                    const int d0 = 8 * I + 2 * r;
-                    if (d0 < N) dst[d0] = acc[I][0];
-                    if (d0 + 1 < N) dst[d0 + 1] = acc[I][1];
                 }
-            }
+            PBTE_STAMP(i0, 10);
             __syncwarp();  // orders the stores of all lanes before lane 0's release
             if (lane == 0)
             {
                 __threadfence_block();
-                atomicOr(s_done + (i >> 5), 1u << (i & 31));
+#pragma unroll
+                for (int t = 0; t < T; ++t) atomicOr(s_done + ((i0 + t) >> 5), 1u << ((i0 + t) & 31));
+            }
+            PBTE_STAMP(i0, 3);
+        };
+        if constexpr (kPairTiles)
+        {
+            // warp w takes the tile pairs (2j, 2j+1), j = w, w + consumers, ...  The pair goes through one pass when the tiles share
+            // their operators and the second does not depend on the first (its last prerequisite, descriptor header word 3, lies
+            // before the pair): then waiting for both cannot block the first.  Otherwise one tile at a time.
+            const int32_t *hdr0 = S.tile_desc + ((size_t)tbase * rows + 1 + F) * kTile;  // header row of the class's first tile
+            for (int j = warp; 2 * j < NT; j += kConsumerWarps)
+            {
+                const int i0 = 2 * j, it = i0 / R;  // R is even: both tiles are in the same round of the ring
+                bool two = false;
+                if (i0 + 1 < NT)
+                {
+                    const int32_t *h0 = hdr0 + (size_t)i0 * rows * kTile, *h1 = h0 + (size_t)rows * kTile;
+                    two = __ldg(h1) == __ldg(h0) && __ldg(h1 + 3) < i0;
+                }
+                PBTE_STAMP(i0, 0);
+                mbar_wait(full + i0 % R, it & 1);
+                if (two) mbar_wait(full + (i0 + 1) % R, it & 1);
+                PBTE_STAMP(i0, 1);
+                if (two) pass(std::integral_constant<int, 2>{}, i0);
+                else
+                {
+                    pass(std::integral_constant<int, 1>{}, i0);
+                    if (i0 + 1 < NT)
+                    {
+                        mbar_wait(full + (i0 + 1) % R, it & 1);
+                        pass(std::integral_constant<int, 1>{}, i0 + 1);
+                    }
+                }
+            }
+        }
+        else
+        {
+            for (int i = warp; i < NT; i += kConsumerWarps)
+            {
+                PBTE_STAMP(i, 0);
+                mbar_wait(full + i % R, (i / R) & 1);
+                PBTE_STAMP(i, 1);
+                pass(std::integral_constant<int, 1>{}, i);
             }
         }
     }

@@ -101,6 +101,39 @@ def test_marching_kernel_without_staged_operators(name, monkeypatch):
     hc.close()
 
 
+@pytest.mark.parametrize("name", ["quad_p1_dim3", "hex_p1", "quad_p2", "quad_p4", "c2_hex_p2_small", "hex_p3"])
+@pytest.mark.parametrize("variant", [0, 1])
+def test_marching_variants_on_single_class_meshes(name, variant, monkeypatch):
+    """Cartesian quads/hexes have one operator class: the marching path then has two kernels, operators staged in shared memory
+    (variant 0) or held in consumer registers (variant 1, sweep_regop.cuh; the library's choice where a slot's operators do not fit
+    half an SM's shared memory, i.e. hex order 3).  Both are forced here on every element size: ndof 4, 8, 9, 25, 27, 64."""
+    monkeypatch.setenv("PBTE_MARCH_REGOP", str(variant))
+    hc = host_case(name)
+    P = hc.problem
+    iters = CASES[name]["iters"]
+    want = orc.solve(P, iters, 0.0, cache_lu=True, threads=8)
+    got = gpu_solve(P, iters, kernel=3)
+    assert got["stats"].kernel_used == 3 and got["stats"].march_variant == variant
+    assert np.array_equal(got["orders"], orc.sweep_orders(P))
+    for k in ("Tc", "Qc", "Tv", "Qv", "coeff"):
+        assert rel(got[k], want[k]) <= TOL[name], (k, rel(got[k], want[k]))
+    hc.close()
+
+
+@pytest.mark.parametrize("name", ["quad_p4", "hex_p3"])
+def test_register_operator_variant_consistent_traces(name, monkeypatch):
+    """The register-operator kernel on the well-conditioned form of the high-order cases: 1e-10 after every iteration."""
+    monkeypatch.setenv("PBTE_MARCH_REGOP", "1")
+    hc = host_case(name, face_rule=1)
+    P = hc.problem
+    want = orc.solve(P, 3, 0.0, cache_lu=False, threads=8)
+    got = gpu_solve(P, 3, kernel=3)
+    assert got["stats"].march_variant == 1
+    for k in ("Tc", "Qc", "Tv", "Qv", "coeff"):
+        assert rel(got[k], want[k]) <= 1e-10, (k, rel(got[k], want[k]))
+    hc.close()
+
+
 def test_marching_kernel_on_refined_simplex_mesh():
     """Refined tetrahedra: 30 operator classes, 28 upwind DAGs, half-empty tiles; compared with the per-element LU kernel
     (the oracle needs minutes here) at 1e-10 after 3 iterations."""
