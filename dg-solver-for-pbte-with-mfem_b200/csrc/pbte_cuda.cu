@@ -137,7 +137,8 @@ struct pbte_handle
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     bool sweep_timed = false;
     int64_t launches = 0, sweeps = 0, launches_per_sweep = 0;
-    double last_sweep_ms = 0.0, last_finish_ms = 0.0;
+    double last_sweep_ms = 0.0, last_finish_ms = 0.0, last_march_ms = 0.0;
+    cudaEvent_t ev_march = nullptr;  // recorded right after the marching kernel (an event-record node when the sweep is a graph)
 
     ~pbte_handle()
     {
@@ -145,6 +146,7 @@ struct pbte_handle
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (ev2) cudaEventDestroy(ev2);
+        if (ev_march) cudaEventDestroy(ev_march);
         if (h_norms) cudaFreeHost(h_norms);
         if (h_flag) cudaFreeHost(h_flag);
         if (own_stream && stream) cudaStreamDestroy(stream);
@@ -410,6 +412,12 @@ int enqueue_sweep(pbte_handle *h, int piv, int64_t *launch_count)
 #endif
         if (h->march_regop) pick_regop_kernel(h->n)<<<h->nslots(), regop_threads(h->n), h->march_smem, h->stream>>>(P, S);
         else pick_march_kernel(h->n, h->march_stage)<<<h->nslots(), march_threads(h->n), h->march_smem, h->stream>>>(P, S);
+        {
+            // inside a stream capture the record must become an event-record NODE (external flag), else it is only a dependency
+            cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+            CK(cudaStreamIsCapturing(h->stream, &cs));
+            CK(cudaEventRecordWithFlags(h->ev_march, h->stream, cs == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault));
+        }
         const size_t block = (size_t)h->ne * h->n, count = (size_t)(1 + h->dim) * block;
         const int chunks = h->mom_chunks, per = (h->nslots() + chunks - 1) / chunks;
         moments_from_flux_kernel<<<dim3((unsigned)((block + 255) / 256), (unsigned)chunks), 256, 0, h->stream>>>(P, chunks > 1 ? h->partial.p : h->mom.p, per);
@@ -723,6 +731,7 @@ int pbte_cuda_create(const pbte_problem_t *p, const pbte_options_t *opt_in, pbte
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
     CK(cudaEventCreate(&h->ev2));
+    CK(cudaEventCreate(&h->ev_march));
     CK(cudaMallocHost(&h->h_norms, 4 * sizeof(double)));
     CK(cudaMallocHost(&h->h_flag, sizeof(int32_t)));
     h->cache_policy = opt.cache_policy;
@@ -1291,6 +1300,12 @@ int pbte_cuda_finish_iteration(pbte_handle_t *h, double *residual)
     {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_sweep_ms = ms;
+        if (h->kernel_used == 3 && cudaEventElapsedTime(&ms, h->ev0, h->ev_march) == cudaSuccess) h->last_march_ms = ms;
+        else
+        {
+            h->last_march_ms = 0.0;
+            (void)cudaGetLastError();
+        }
         if (cudaEventElapsedTime(&ms, h->ev1, h->ev2) == cudaSuccess) h->last_finish_ms = ms;
     }
     h->last_tv_norm = std::sqrt(t2);
@@ -1416,6 +1431,7 @@ int pbte_cuda_get_stats(pbte_handle_t *h, pbte_stats_t *s)
     s->kernel_launches = h->launches;
     s->sweeps = h->sweeps;
     s->last_sweep_ms = h->last_sweep_ms;
+    s->last_march_ms = h->last_march_ms;
     s->last_finish_ms = h->last_finish_ms;
     s->flux_bytes = (int64_t)(h->flux.count * sizeof(double));
     s->launches_per_sweep = h->launches_per_sweep;

@@ -185,6 +185,7 @@ typedef struct pbte_stats
     int32_t march_variant;    /* marching path: 0 operators in shared memory, 1 operators in registers */
     double march_fill;        /* elements / (8 * tiles): occupancy of the MMA row blocks               */
     int64_t operator_bytes;   /* device bytes of the precomputed shared operators                      */
+    double last_march_ms;     /* device time of the marching kernel alone inside the last sweep (0 = n/a) */
 } pbte_stats_t;
 int pbte_cuda_get_stats(pbte_handle_t *h, pbte_stats_t *stats);
 /* The cudaStream_t the handle launches on (for CUDA-event timing by the caller). */

@@ -14,6 +14,10 @@ CONFIGS = {
     "c4_hex_p3_r1_40bands_32dirs": ("unit-cube-hex", 3, 1, 3, 4, 8, BC3, 20),     # C4 two levels coarser
     "c5_quad_p4_r3_40bands_64dirs": ("unit-square-quad", 4, 3, 2, 1, 64, BC2, 20),  # C5 two levels coarser
     "c2_hex_p2_r2": ("unit-cube-hex", 2, 2, 3, 8, 16, BC3, 1),
+    # full-size single-GPU points
+    "c3_tet_p2_r3_40bands_16dirs_FULL_GPU_SLICE": ("unit-cube-tet", 2, 3, 3, 2, 8, BC3, 20),   # exactly one GPU's share of C3: 196608 tets, 640 slots, 10 GB
+    "c4_hex_p3_r2_40bands_512dirs_1GPU_POINT": ("unit-cube-hex", 3, 2, 3, 16, 32, BC3, 20),    # C4's 1-GPU strong-scaling point: 4096 hexes, 43 GB
+    "c5_quad_p4_r5_40bands_64dirs_FULL": ("unit-square-quad", 4, 5, 2, 1, 64, BC2, 20),        # all of C5: 65536 quads, 2560 slots, 33.5 GB
 }
 names = sys.argv[1:] or list(CONFIGS)
 for name in names:
@@ -39,9 +43,10 @@ for name in names:
             ms.append(s.stats().last_sweep_ms)
         st = s.stats()
         t = float(np.median(ms[2:]))
+        tm = st.last_march_ms
         U = P.updates_per_sweep
         print(f"{name}: ne {P.ne} ndof {P.ndof} slots {P.ndir * P.nband} kernel {st.kernel_used} dag-classes {st.n_classes} levels {st.max_levels} "
               f"op-classes {st.n_operator_classes} fill {st.march_fill:.2f} flux {st.flux_bytes / 1e9:.2f} GB ops {st.operator_bytes / 1e6:.0f} MB | "
-              f"host {t_host:.1f}s setup {t_setup:.1f}s sweep {t:.3f} ms -> {U / t / 1e6:.1f} M updates/ms", flush=True)
+              f"variant {st.march_variant} host {t_host:.1f}s setup {t_setup:.1f}s sweep {t:.3f} ms (marching kernel {tm:.3f}) -> {U / t / 1e6:.1f} M updates/ms", flush=True)
         s.close()
     hc.close()
