@@ -71,22 +71,40 @@ def load_measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
+_SAMPLER_SRC = r"""
+import sys, time, select
+idx = int(sys.argv[1])
+rows = []
+try:
+    import pynvml as nv
+    nv.nvmlInit()
+    h = nv.nvmlDeviceGetHandleByIndex(idx)
+    mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+    get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+    print("ready nvml", mx, flush=True)
+    while not select.select([sys.stdin], [], [], 0.001)[0]:
+        rows.append((time.time(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), int(get_reasons(h))))
+except Exception as ex:
+    print("ready none 0", flush=True)
+for r in rows:
+    print(*r)
+"""
+
+
 class ClockSampler:
     """SM clock and throttle reasons DURING the timed region.  The timed region of the default run lasts ~10 ms, far below the
     100 ms period of the recipe's `nvidia-smi -lms` line (B200_PROFILING.md), so the same counters are read through NVML
-    (nvidia_ml_py) from a thread that polls as fast as the driver answers (~0.1 ms per query); `nvidia-smi` is the fallback."""
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
-        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    (nvidia_ml_py) every ~1 ms.  The polling runs in a CHILD process that keeps its samples in memory until it is told to stop:
+    a polling thread inside this process competes with the launching thread for the interpreter lock and stretched the
+    host-side gaps of rank 0 at N > 1 by 0.3 ms per step.  Samples are time-stamped; only those inside the timed region count."""
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.sm, self.mx, self.reasons = [], [], set()
         self.proc = None
-        self.nvml = None
-        self.handle = None
-        self.running = False
-        self.thread = None
         self.source = None
+        self.max_mhz = None
+        self.t0 = self.t1 = None
 
     def _physical_index(self):
         vis = os.environ.get("CUDA_VISIBLE_DEVICES")
@@ -96,74 +114,42 @@ class ClockSampler:
                 return int(ids[self.gpu])
         return self.gpu
 
-    def start(self):
+    def launch(self):
+        """Start the child (before the warm-up: it needs ~0.2 s to import NVML); returns once it is polling."""
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nvml = pynvml
-            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
-            self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)))
-            self.source = "nvml"
-            self.running = True
-            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
-            self.thread.start()
-            return
-        except Exception:
-            self.nvml = None
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self._physical_index())],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.source = "nvidia-smi"
-            self.thread = threading.Thread(target=self._read_smi, daemon=True)
-            self.thread.start()
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(self._physical_index())], stdin=subprocess.PIPE, stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            first = self.proc.stdout.readline().split()
+            self.source = first[1] if len(first) > 1 else "none"
+            self.max_mhz = float(first[2]) if len(first) > 2 else None
         except Exception:
             self.proc = None
 
-    def _poll_nvml(self):
-        nv = self.nvml
-        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
-                "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
-                "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
-                "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
-        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
-        while self.running:
-            try:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
-                mask = int(get_reasons(self.handle))
-                for name, bit in bits.items():
-                    if mask & bit:
-                        self.reasons.add(name)
-            except Exception:
-                break
-
-    def _read_smi(self):
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.proc.stdout:
-            r = [x.strip() for x in line.split(",")]
-            try:
-                self.sm.append(float(r[1]))
-                self.mx.append(float(r[2]))
-                for name, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        self.reasons.add(name)
-            except Exception:
-                continue
+    def start(self):
+        self.t0 = time.time()
 
     def stop(self):
-        if self.nvml is not None:
-            self.running = False
-            self.thread.join(2)
-        elif self.proc is not None:
-            time.sleep(0.05)
-            self.proc.terminate()
-            try:
-                self.proc.wait(2)
-            except Exception:
-                self.proc.kill()
-        else:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["neither NVML nor nvidia-smi available"], "samples": 0}
-        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
-                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source}
+        self.t1 = time.time()
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML sampler could not start"], "samples": 0}
+        try:
+            out, _ = self.proc.communicate("stop\n", timeout=10)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, reasons = [], set()
+        for line in out.splitlines():
+            f = line.split()
+            if len(f) != 3:
+                continue
+            t, mhz, mask = float(f[0]), float(f[1]), int(f[2])
+            if self.t0 <= t <= self.t1:
+                sm.append(mhz)
+                for name, bit in self.BITS.items():
+                    if mask & bit:
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons), "samples": len(sm),
+                "source": self.source, "window_ms": (self.t1 - self.t0) * 1e3}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -265,9 +251,17 @@ def run_gpu(args, rank, world, local_rank):
         raise RuntimeError("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dist = None
+    saved_stdout = None
     if world > 1:
+        # NCCL prints its version banner on stdout when a communicator is created: keep stdout for the one JSON line by pointing
+        # fd 1 at stderr until the warm-up is over
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         import torch.distributed as dist_mod
         dist = dist_mod
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keeps NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
 
     azim = WORKLOAD["azimuth"] * world
@@ -286,10 +280,18 @@ def run_gpu(args, rank, world, local_rank):
             __cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 3, "strides": None}
         mom = torch.as_tensor(_Buf(), device=torch.device("cuda", local_rank))
 
+    phase_ev = []  # BENCH_PHASES=1: CUDA events around the all-reduce of every step (diagnostics on stderr)
+
     def step():
         solver.sweep()
         if mom is not None:
-            with torch.cuda.stream(stream):
+            if os.environ.get("BENCH_PHASES"):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                dist.all_reduce(mom, op=dist.ReduceOp.SUM)
+                e1.record(stream)
+                phase_ev.append((e0, e1))
+            else:
                 dist.all_reduce(mom, op=dist.ReduceOp.SUM)
         return solver.finish_iteration()
 
@@ -298,11 +300,17 @@ def run_gpu(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.launch()
     with torch.cuda.stream(stream):
         for _ in range(max(args.warmup, 3)):
             step()
         barrier()
-        sampler = ClockSampler(local_rank)
+        if saved_stdout is not None:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
         if rank == 0:
             sampler.start()
         st0 = solver.stats()
@@ -319,6 +327,10 @@ def run_gpu(args, rank, world, local_rank):
         clocks = sampler.stop() if rank == 0 else None
         st1 = solver.stats()
     total_ms = ev0.elapsed_time(ev1)
+    if phase_ev:
+        ar = [a.elapsed_time(b) for a, b in phase_ev[-args.steps:]]
+        print(f"[rank {rank}] phases per step: sweep {np.mean(sweep_ms):.3f} ms, all-reduce (device, incl. waiting for the peers) {np.mean(ar):.3f} ms "
+              f"(min {min(ar):.3f}), finish {solver.stats().last_finish_ms:.3f} ms, step {total_ms / args.steps:.3f} ms", file=sys.stderr, flush=True)
     t = torch.tensor([total_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
