@@ -34,6 +34,15 @@ UNIT = "updates/s"
 BC3 = {1: -0.5, 2: -0.5, 3: -0.5, 4: -0.5, 5: -0.5, 6: 0.5}
 WORKLOAD = dict(mesh="unit-cube-hex", order=2, refine=2, angle_dim=3, polar=8, azimuth=16, num_spectral=1)
 SAMPLE = dict(WORKLOAD, refine=1)  # CPU legs: same workload one refinement level down (512 hexes), updates/s is size independent
+# --workload: the other BASELINE configs at their real sizes (extra measurements, profiles/README.md; the default stays C2, the
+# configuration the metric is quoted on).  C2 is weak-scaled (128 directions per GPU); these keep the named quadrature and split
+# its directions over the GPUs (strong scaling)
+EXTRA_WORKLOADS = {
+    "c3": dict(mesh="unit-cube-tet", order=2, refine=3, angle_dim=3, polar=8, azimuth=16, num_spectral=20,
+               label="C3: builtin unit-cube-tet refine 3 (196608 tets), DG order 2 (ndof 10), 8 x 16 = 128 directions, non-gray Si = 40 bands"),
+    "c4": dict(mesh="unit-cube-hex", order=3, refine=2, angle_dim=3, polar=16, azimuth=32, num_spectral=20,
+               label="C4 (1-GPU strong-scaling point of SURVEY 8d): unit-cube-hex refine 2 (4096 hexes), DG order 3 (ndof 64), 16 x 32 = 512 directions, 40 bands"),
+}
 
 
 def flops_per_update(n, dim, faces):
@@ -264,9 +273,10 @@ def run_gpu(args, rank, world, local_rank):
             os.environ["NCCL_DEBUG"] = "WARN"  # keeps NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
 
-    azim = WORKLOAD["azimuth"] * world
-    hc = pb.HostCase(WORKLOAD["mesh"], WORKLOAD["order"], WORKLOAD["refine"], WORKLOAD["angle_dim"], WORKLOAD["polar"], azim, True, False, BC3,
-                     num_spectral=WORKLOAD["num_spectral"])
+    wl = EXTRA_WORKLOADS.get(args.workload, WORKLOAD)
+    strong = args.workload in EXTRA_WORKLOADS
+    azim = wl["azimuth"] * (1 if strong else world)
+    hc = pb.HostCase(wl["mesh"], wl["order"], wl["refine"], wl["angle_dim"], wl["polar"], azim, True, False, BC3, num_spectral=wl["num_spectral"])
     P = hc.problem
     k0, k1 = pb.partition_directions(P.ndir, world, rank)
     stream = torch.cuda.Stream(device=local_rank)
@@ -368,7 +378,7 @@ def run_gpu(args, rank, world, local_rank):
     # ---- the kept C++ API call, PBTESolver::Solve(coeff, macro), with its full host-state upload/download (N = 1 only) --
     solve_call = None
     general = None
-    if world == 1 and st1.kernel_used == 3 and not args.no_general:
+    if world == 1 and st1.kernel_used == 3 and not args.no_general and not strong:
         # the per-element LU path (any mesh) timed on the same workload, for the record
         solver.close()
         g = pb.Solver(P, device=local_rank, dir_range=(k0, k1), cache_policy=0, kernel=2, stream=stream.cuda_stream)
@@ -385,7 +395,7 @@ def run_gpu(args, rank, world, local_rank):
         general = {"kernel": "warp-register (one pivoted LU per (element, direction, band); any mesh)", "value": U / gs, "unit": UNIT,
                    "sweep_ms": gs * 1e3, "flop_per_update": gf, "fp64_tflops": gf * U / gs / 1e12}
         g.close()
-    if world == 1:
+    if world == 1 and not strong:  # (the extra workloads hold up to 80 GB of flux: no host copy of it)
         solver.close()
         hs = pb.HostSolver(hc, 0)
         hs.solve(1)
@@ -441,9 +451,10 @@ def run_gpu(args, rank, world, local_rank):
     flux_mb = P.ndof * P.ne * (k1 - k0) * P.nband * 8 / 1e6
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C2: builtin unit-cube-hex refine 2 ({P.ne} hexes), DG order 2 (ndof {P.ndof}), 8 Gauss polar x {azim} uniform azimuth = {P.ndir} directions"
-                               f" ({k1 - k0} per GPU), gray SMRT = 2 bands, reference-compatible local matrices; {U} updates per step",
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": (f"{wl['label']} ({k1 - k0} directions on this GPU), reference-compatible local matrices; {U} updates per step" if strong else
+                                f"C2: builtin unit-cube-hex refine 2 ({P.ne} hexes), DG order 2 (ndof {P.ndof}), 8 Gauss polar x {azim} uniform azimuth = {P.ndir} directions"
+                                f" ({k1 - k0} per GPU), gray SMRT = 2 bands, reference-compatible local matrices; {U} updates per step"),
                    "parallelism": f"directions partitioned over {world} GPU(s), one FP64 all-reduce of [Tc|Qc] per step" if world > 1 else "single GPU",
                    "l2_flush": f"none needed: the flux ({flux_mb:.0f} MB per GPU) is read and rewritten every step and exceeds the 126 MB L2",
                    "schedule": sched,
@@ -463,7 +474,7 @@ def run_gpu(args, rank, world, local_rank):
     }
     if general is not None:
         line["general_path"] = general
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not strong:
         try:
             line["cpu_baseline"] = cpu_baseline_leg()
         except Exception as ex:  # the CPU leg must never take the GPU numbers down with it
@@ -479,6 +490,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2"] + sorted(EXTRA_WORKLOADS), help="c2 = the benchmark; c3/c4 = extra full-size measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-general", action="store_true", help="skip the side measurement of the per-element LU kernel")
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 warp-register, 3 shared-operator marching")

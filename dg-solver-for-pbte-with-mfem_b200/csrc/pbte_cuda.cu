@@ -567,9 +567,11 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
     auto ring_for = [&](size_t budget, bool stage, int *ring) {
         const size_t fixed = (stage ? stage_bytes : 0) + 64;
         // mbarrier parity waits are only valid within one phase of the barrier: a slot is always refilled by the same producer
-        // warp (ring size a multiple of the producer warps per role) and the ring holds at least one tile per consumer warp (a
-        // consumer must find the slot of its next tile at most one phase behind)
-        for (int r = 16; r >= march_min_ring(n); r -= 2)
+        // warp (ring size a multiple of the producer warps per role: a warp works in order, so the slot's previous tile is loaded
+        // before it waits for the slot again) and the ring holds at least one tile per consumer warp (a consumer must find the
+        // slot of its next tile at most one phase behind).  A ring that breaks the first rule hangs on large meshes.
+        const int step = march_role_warps(n) % 2 == 0 ? march_role_warps(n) : 2 * march_role_warps(n);
+        for (int r = 16 / step * step; r >= march_min_ring(n) && r > 0; r -= step)
             if (fixed + march_meta_bytes(sched.max_levels, noc, r, sched.max_class_tiles, h_doubles) + (size_t)r * slot_bytes <= budget)
             {
                 *ring = r;

@@ -372,10 +372,15 @@ __host__ __device__ constexpr int march_consumers(int n) { return n <= 36 ? (mar
 // ring slots a CTA needs at least: one per tile a consumer warp can hold (an mbarrier parity wait is only meaningful within one
 // phase of its barrier: a consumer must find the slot of its next tile at most one phase behind)
 __host__ __device__ constexpr int march_min_ring(int n) { return march_consumers(n) * (march_pair_tiles(n) ? 2 : 1); }
-constexpr int kSrcWarps = 2;       // source loaders (run ahead of the wavefront); warp p takes tiles p, p + kSrcWarps, ...
-constexpr int kNbrWarps = 2;       // upwind-neighbour loaders (follow the wavefront), same interleaving
-static_assert(kSrcWarps == 2 && kNbrWarps == 2, "ring sizes are chosen even so that every slot has one producer warp per role");
-__host__ __device__ constexpr int march_threads(int n) { return (march_consumers(n) + kSrcWarps + kNbrWarps) * 32; }
+// Producer warps per role (source loaders run ahead of the wavefront, upwind-neighbour loaders follow it); warp p of a role takes
+// tiles p, p + warps, ...  A producer warp needs ~1000 cycles per tile whatever the tile's size (the copies of a tile are issued and
+// tracked at memory latency, profiles/README.md), a consumer warp needs ~50 cycles per MMA: small elements (tets order 2: 24 MMAs
+// per tile) are bound by the producers and get four warps per role, large ones two.
+#ifndef PBTE_SMALL_PRODUCERS
+#define PBTE_SMALL_PRODUCERS 4
+#endif
+__host__ __device__ constexpr int march_role_warps(int n) { return n <= 16 ? PBTE_SMALL_PRODUCERS : 2; }
+__host__ __device__ constexpr int march_threads(int n) { return (march_consumers(n) + 2 * march_role_warps(n)) * 32; }
 
 // shared-memory row stride (doubles) of a staged element vector: 4*KS rounded so that the four element rows a half warp reads
 // with one LDS.64 fall into disjoint bank groups (stride mod 16 in {4, 12})
@@ -415,6 +420,7 @@ template <int N, bool STAGE>
 __global__ void __launch_bounds__(march_threads(N), N <= 36 ? 2 : 1) sweep_march_kernel(DevProblem P, DevMarch S)
 {
     constexpr int kConsumerWarps = march_consumers(N);
+    constexpr int kSrcWarps = march_role_warps(N), kNbrWarps = march_role_warps(N);
     constexpr bool kPairTiles = march_pair_tiles(N);
     using G = Frag<N>;
     constexpr int MT = G::MT, MP = G::MP, KS = G::KS, FR = G::FR;
