@@ -632,14 +632,34 @@ __global__ void __launch_bounds__(march_threads(N), N <= 36 ? 2 : 1) sweep_march
             // what the descriptors say about the inflow faces: the wall faces of this lane's elements, and the faces where some
             // element of the pass has an interior upwind neighbour
             unsigned interior = 0;
-            for (int m = 0; m < nin; ++m)
+            {
+                // rows 1..kMaxIn of a descriptor always exist (rows = 2 + F, F >= 3): read them all at once, then vote
+                int code[T][kMaxIn];
 #pragma unroll
                 for (int t = 0; t < T; ++t)
+#pragma unroll
+                    for (int m = 0; m < kMaxIn; ++m) code[t][m] = sd[t][(1 + m) * kTile + q];
+#pragma unroll
+                for (int m = 0; m < kMaxIn; ++m)
                 {
-                    const int code = sd[t][(1 + m) * kTile + q];
-                    wall[t] |= (unsigned)(code == kSrcWallCode) << m;
-                    interior |= (unsigned)(__ballot_sync(0xffffffffu, code >= 0) != 0u) << m;
+                    bool any = false;
+#pragma unroll
+                    for (int t = 0; t < T; ++t)
+                    {
+                        wall[t] |= (unsigned)(code[t][m] == kSrcWallCode && m < nin) << m;
+                        any = any || code[t][m] >= 0;
+                    }
+                    interior |= (unsigned)(__ballot_sync(0xffffffffu, any && m < nin) != 0u) << m;
                 }
+                for (int m = kMaxIn; m < nin; ++m)  // elements with more inflow faces than any supported shape has today
+#pragma unroll
+                    for (int t = 0; t < T; ++t)
+                    {
+                        const int c2m = sd[t][(1 + m) * kTile + q];
+                        wall[t] |= (unsigned)(c2m == kSrcWallCode) << m;
+                        interior |= (unsigned)(__ballot_sync(0xffffffffu, c2m >= 0) != 0u) << m;
+                    }
+            }
             double acc[T][MT][2];
 #pragma unroll
             for (int t = 0; t < T; ++t)
