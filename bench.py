@@ -407,6 +407,27 @@ def run_gpu(args, rank, world, local_rank):
                       "note": "one Solve(coeff, macro) call on host DenseMatrix blocks: flux uploaded at entry and downloaded at exit (pageable memory)"}
         hs.close()
 
+    # ---- seconds to converged T (the second half of BASELINE.json's metric), N = 1 -------------------------------------
+    # With the reference's own face rule the source iteration DIVERGES on this order-2 hex mesh (Tc overflows
+    # after a few hundred iterations, in the reference's CPU code as well: DESIGN.md section 4), so the time to a converged field is
+    # measured on the same mesh and quadrature with consistent face traces, to the reference's default tolerance 1e-8.
+    converged = None
+    if world == 1 and not strong:
+        hcc = pb.HostCase(wl["mesh"], wl["order"], wl["refine"], wl["angle_dim"], wl["polar"], azim, True, False, BC3, face_rule=1, num_spectral=wl["num_spectral"])
+        sc = pb.Solver(hcc.problem, device=local_rank, cache_policy=0, kernel=args.kernel)
+        sc.build_schedule()
+        t0 = time.perf_counter()
+        try:
+            iters, resid, _ = sc.solve(5000, 1e-8)
+            dt = time.perf_counter() - t0
+            converged = {"seconds": dt, "iterations": int(iters), "residual": float(resid), "tol": 1e-8, "updates_per_s": U * iters / dt,
+                         "what": "pbte_cuda_solve from zero initial state until |Tv - Tv_prev| / |Tv| < 1e-8; C2 mesh and quadrature, consistent face traces"
+                                 " (the reference's face rule diverges here)"}
+        except pb.PbteError as ex:
+            converged = {"error": str(ex)}
+        sc.close()
+        hcc.close()
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -474,6 +495,8 @@ def run_gpu(args, rank, world, local_rank):
     }
     if general is not None:
         line["general_path"] = general
+    if converged is not None:
+        line["time_to_converged_T"] = converged
     if world == 1 and not args.no_cpu_baseline and not strong:
         try:
             line["cpu_baseline"] = cpu_baseline_leg()
