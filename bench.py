@@ -91,7 +91,7 @@ try:
     mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
     get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
     print("ready nvml", mx, flush=True)
-    while not select.select([sys.stdin], [], [], 0.001)[0]:
+    while not select.select([sys.stdin], [], [], 0.0002)[0]:
         rows.append((time.time(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), int(get_reasons(h))))
 except Exception as ex:
     print("ready none 0", flush=True)
@@ -103,7 +103,7 @@ for r in rows:
 class ClockSampler:
     """SM clock and throttle reasons DURING the timed region.  The timed region of the default run lasts ~10 ms, far below the
     100 ms period of the recipe's `nvidia-smi -lms` line (B200_PROFILING.md), so the same counters are read through NVML
-    (nvidia_ml_py) every ~1 ms.  The polling runs in a CHILD process that keeps its samples in memory until it is told to stop:
+    (nvidia_ml_py) as fast as the driver answers (a few queries per millisecond at best).  The polling runs in a CHILD process that keeps its samples in memory until it is told to stop:
     a polling thread inside this process competes with the launching thread for the interpreter lock and stretched the
     host-side gaps of rank 0 at N > 1 by 0.3 ms per step.  Samples are time-stamped; only those inside the timed region count."""
     BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
