@@ -1,5 +1,5 @@
 """Development probe: per-tile clock stamps of CTA 0 of the marching kernel on the C2 mesh (needs the -DPBTE_TRACE build of the
-CUDA library: PBTE_LIB_DIR=tools/_trace).  usage: trace_probe.py <azimuth> <out file>"""
+CUDA library: PBTE_LIB_DIR=tools/_trace).  usage: trace_probe.py <azimuth> <out file> [tet]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (os.path.join(ROOT, "dg-solver-for-pbte-with-mfem_b200"), os.path.join(ROOT, "tests")):
@@ -8,7 +8,10 @@ import pbte_b200 as pb
 from cases import BC3
 
 azim, out = int(sys.argv[1]), sys.argv[2]
-hc = pb.HostCase("unit-cube-hex", 2, 2, 3, 8, azim, True, False, BC3, num_spectral=1)
+if len(sys.argv) > 3 and sys.argv[3] == "tet":  # a slice of C3 one level coarser: 24576 tets order 2, 2 x azim directions x 40 bands
+    hc = pb.HostCase("unit-cube-tet", 2, 2, 3, 2, azim, True, False, BC3, num_spectral=20)
+else:
+    hc = pb.HostCase("unit-cube-hex", 2, 2, 3, 8, azim, True, False, BC3, num_spectral=1)
 s = pb.Solver(hc.problem, kernel=3)
 s.build_schedule()
 for i in range(4):
