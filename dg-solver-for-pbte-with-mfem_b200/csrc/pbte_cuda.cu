@@ -114,6 +114,8 @@ struct pbte_handle
     bool march_regop = false;  // one operator class: operators in consumer registers (sweep_regop.cuh)
     int march_h_smem = 0;
     int march_ring = 0, march_nv = 0;  // tile-ring slots per CTA, staged vectors per slot
+    bool march_compact = false;        // operators stored compact (row-major n x n) instead of in MMA fragment order
+    int march_op_stride = 0;           // doubles per operator in m_ops
     int mom_chunks = 1;  // slot chunks of the moment pass
     size_t march_smem = 0;
     DevBuf<int32_t> m_slot_class, m_cls_level_begin, m_level_tile_begin, m_tile_oclass, m_tile_desc, m_cls_op_off, m_cls_op_cnt, m_oc_rep,
@@ -286,6 +288,8 @@ DevMarch make_dev_march(pbte_handle *h)
     S.noclass = h->plan.noclass;
     S.h_smem = h->march_h_smem;
     S.ring = h->march_ring;
+    S.op_stride = h->march_op_stride;
+    S.op_compact = h->march_compact ? 1 : 0;
     S.nv = h->march_nv;
     S.F = h->F;
     S.slot_class = h->m_slot_class.p;
@@ -507,18 +511,11 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
         }
         op_cnt[c] = cnt;
     }
-    std::vector<unsigned long long> slot_base(ns);
-    size_t total = 0;
     int max_cnt = 0;
     for (int c = 0; c < nclass; ++c)
     {
         max_cnt = std::max(max_cnt, (int)op_cnt[c]);
-        for (int s = h->cls_slot_begin[c]; s < h->cls_slot_begin[c + 1]; ++s)
-        {
-            slot_class[s] = c;
-            slot_base[s] = total;
-            total += (size_t)op_cnt[c] * FR;
-        }
+        for (int s = h->cls_slot_begin[c]; s < h->cls_slot_begin[c + 1]; ++s) slot_class[s] = c;
     }
     int st;
     if ((st = upload(h->m_slot_class, slot_class.data(), slot_class.size(), h->stream))) return st;
@@ -529,7 +526,6 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
     if ((st = upload(h->m_cls_inmask, sched.cls_inmask.data(), sched.cls_inmask.size(), h->stream))) return st;
     if ((st = upload(h->m_cls_op_off, op_off.data(), op_off.size(), h->stream))) return st;
     if ((st = upload(h->m_cls_op_cnt, op_cnt.data(), op_cnt.size(), h->stream))) return st;
-    if ((st = upload(h->m_slot_op_base, slot_base.data(), slot_base.size(), h->stream))) return st;
     if ((st = upload(h->m_oc_rep, plan.oc_rep.data(), plan.oc_rep.size(), h->stream))) return st;
     if ((st = upload(h->m_oc_ksrc, plan.oc_ksrc.data(), plan.oc_ksrc.size(), h->stream))) return st;
     if ((st = upload(h->m_oc_gsrc, plan.oc_gsrc.data(), plan.oc_gsrc.size(), h->stream))) return st;
@@ -544,7 +540,6 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
         if ((st = upload(h->m_ctbc, tb.data(), tb.size(), h->stream))) return st;
         CK(cudaStreamSynchronize(h->stream));
     }
-    CK(h->m_ops.alloc(total));
     const size_t nh = (size_t)ns * noc * F * n;
     CK(h->m_oph.alloc(nh));
     CK(cudaMemsetAsync(h->m_oph.p, 0, nh * sizeof(double), h->stream));
@@ -620,6 +615,22 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
     }
     h->march_ring = ring;
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->march_smem));
+    {
+        // operator storage: fragment order where a CTA stages its slot's block (or keeps it in registers), compact row-major where
+        // every tile reads its operators from global memory
+        h->march_compact = !h->march_stage && !h->march_regop;
+        h->march_op_stride = h->march_compact ? compact_doubles(n) : (int)FR;
+        std::vector<unsigned long long> slot_base(ns);
+        size_t total = 0;
+        for (int s = 0; s < ns; ++s)
+        {
+            slot_base[s] = total;
+            total += (size_t)op_cnt[slot_class[s]] * h->march_op_stride;
+        }
+        if ((st = upload(h->m_slot_op_base, slot_base.data(), slot_base.size(), h->stream))) return st;
+        CK(h->m_ops.alloc(total));
+        CK(cudaStreamSynchronize(h->stream));
+    }
 
     const size_t build_smem = 2 * (size_t)n * n * sizeof(double);
     if (build_smem > (size_t)max_optin || n > 128) return fail(PBTE_ERR_INVALID, "ndof too large for the operator construction kernel");

@@ -36,7 +36,9 @@ struct DevMarch
     const int32_t *tile_oclass;       // [ntiles]
     const int32_t *tile_desc;         // [ntiles][1+F][8]
     const uint8_t *cls_inmask;        // [nclass][noclass] canonical inflow faces
-    const int32_t *cls_op_off;        // [nclass][noclass] first operator of the class inside a slot's operator block (units of FR)
+    int op_stride;                    // doubles per operator in ops: frag_doubles(n) (fragment order) or compact_doubles(n) (op_compact)
+    int op_compact;                   // 1: operators stored row-major n x n (operators that are never staged: many operator classes)
+    const int32_t *cls_op_off;        // [nclass][noclass] first operator of the class inside a slot's operator block (units of op_stride)
     const int32_t *cls_op_cnt;        // [nclass] operators per slot
     const unsigned long long *slot_op_base;  // [nslots] offset (doubles) of the slot's operator block in ops
     double *ops;                      // operators in MMA fragment order
@@ -60,6 +62,11 @@ struct Frag
     static constexpr int FR = MP * KS * 64;  // doubles per operator in fragment order
 };
 __host__ __device__ inline int frag_doubles(int n) { return ((((n + 7) / 8) + 1) / 2) * ((n + 3) / 4) * 64; }
+// Compact storage, row-major n x n rounded to an even count: used when the operators are read from global memory by every tile
+// (meshes with many operator classes).  Fragment order pads ndof 10 to 16 x 12 (192 doubles against 100); there the operator
+// fragments are most of what the kernel reads from DRAM (ncu on C3: 777 GB per sweep against 80 GB of flux), so the padding
+// goes.
+__host__ __device__ constexpr int compact_doubles(int n) { return (n * n + 1) & ~1; }
 
 // thread j solves column j of R in place with the row-pivoted LU factors in A (swaps, unit-lower forward, upper backward)
 __device__ __forceinline__ void lu_solve_columns(const double *A, double *R, const int *piv, int n, int ncol)
@@ -191,7 +198,13 @@ __global__ void __launch_bounds__(128) build_operators_kernel(DevProblem P, DevM
         __syncthreads();
     }
 
-    double *ops = S.ops + S.slot_op_base[s] + (size_t)S.cls_op_off[(size_t)c * S.noclass + o] * FR;
+    const int OPS = S.op_stride;
+    double *ops = S.ops + S.slot_op_base[s] + (size_t)S.cls_op_off[(size_t)c * S.noclass + o] * OPS;
+    auto store_operator = [&](double *out, const double *Rm) {
+        if (S.op_compact)
+            for (int idx = t; idx < OPS; idx += T) out[idx] = idx < n * n ? Rm[idx / n + (size_t)(idx % n) * n] : 0.0;  // row-major
+        else store_fragment_order(out, Rm, n);
+    };
     // P = A^-1 M^T
     {
         const double *MTe = P.massT + (size_t)e * ms;
@@ -199,7 +212,7 @@ __global__ void __launch_bounds__(128) build_operators_kernel(DevProblem P, DevM
         __syncthreads();
         lu_solve_columns(A, R, s_piv, n, n);
         __syncthreads();
-        store_fragment_order(ops, R, n);
+        store_operator(ops, R);
         __syncthreads();
     }
     int m = 1;
@@ -208,7 +221,7 @@ __global__ void __launch_bounds__(128) build_operators_kernel(DevProblem P, DevM
         if (!(inm >> j & 1u)) continue;
         const double cin = 0.5 * v * (s_af[j] - fabs(s_af[j]));  // c_f (src/PBTESolver.cpp:282)
         const int ks = S.oc_ksrc[(size_t)o * F + j], gs = S.oc_gsrc[(size_t)o * F + j];
-        double *out = ops + (size_t)m * FR;
+        double *out = ops + (size_t)m * OPS;
         if (ks >= 0)
         {
             // Q_j = -c_j A^-1 K_j
@@ -217,10 +230,10 @@ __global__ void __launch_bounds__(128) build_operators_kernel(DevProblem P, DevM
             __syncthreads();
             lu_solve_columns(A, R, s_piv, n, n);
             __syncthreads();
-            store_fragment_order(out, R, n);
+            store_operator(out, R);
         }
         else
-            for (int idx = t; idx < FR; idx += T) out[idx] = 0.0;  // no element of the class has an interior face j
+            for (int idx = t; idx < OPS; idx += T) out[idx] = 0.0;  // no element of the class has an interior face j
         __syncthreads();
         if (gs >= 0)
         {
@@ -424,6 +437,7 @@ __global__ void __launch_bounds__(march_threads(N), N <= 36 ? 2 : 1) sweep_march
     constexpr bool kPairTiles = march_pair_tiles(N);
     using G = Frag<N>;
     constexpr int MT = G::MT, MP = G::MP, KS = G::KS, FR = G::FR;
+    constexpr int OPS = STAGE ? FR : compact_doubles(N);  // doubles per operator: staged operators are in fragment order, others compact
     constexpr int NP = (N + 1) & ~1;        // global row stride (doubles): 16-byte aligned rows
     constexpr int NS = stage_stride(N);     // shared-memory row stride
     constexpr int CH = NP / 2;              // 16-byte chunks per row
@@ -628,14 +642,14 @@ __global__ void __launch_bounds__(march_threads(N), N <= 36 ? 2 : 1) sweep_march
             const int o = sd[0][(1 + F) * kTile];
             const unsigned inm = (unsigned)s_inm[o];
             const int nin = __popc(inm);
-            const double *op = ops + (size_t)s_opoff[o] * FR;
+            const double *op = ops + (size_t)s_opoff[o] * OPS;
             if (!STAGE)
             {
                 // operators of many classes stay in global memory (L2): ask for all of this pass's fragments now, one cache line per
                 // lane and round, so that the later matrix blocks find them in L1 instead of paying an L2 round trip each (C3 slice:
                 // 30.1 -> 26.9 ms per sweep; asking one pass earlier, for the warp's next tile, evicts too much: 29.7 ms)
                 const char *pb = reinterpret_cast<const char *>(op);
-                const int bytes = (1 + nin) * FR * (int)sizeof(double);
+                const int bytes = (1 + nin) * OPS * (int)sizeof(double);
                 for (int off = lane * 128; off < bytes; off += 32 * 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(pb + off));
             }
             // what the descriptors say about the inflow faces: the wall faces of this lane's elements, and the faces where some
@@ -686,7 +700,17 @@ __global__ void __launch_bounds__(march_threads(N), N <= 36 ? 2 : 1) sweep_march
                         if (k0 + k < KS)
                         {
 #pragma unroll
-                            for (int Ip = 0; Ip < MP; ++Ip) bq[k][Ip] = STAGE ? bp[(Ip * KS + k0 + k) * 32] : __ldg(bp + (Ip * KS + k0 + k) * 32);
+                            for (int Ip = 0; Ip < MP; ++Ip)
+                            {
+                                if constexpr (STAGE) bq[k][Ip] = bp[(Ip * KS + k0 + k) * 32];
+                                else
+                                {
+                                    // compact row-major operator: this lane's B entries of row blocks 2Ip and 2Ip+1 are R[row][col]
+                                    const int row = 16 * Ip + q, col = 4 * (k0 + k) + r;
+                                    bq[k][Ip].x = (row < N && col < N) ? __ldg(opb + row * N + col) : 0.0;
+                                    bq[k][Ip].y = (row + 8 < N && col < N) ? __ldg(opb + (row + 8) * N + col) : 0.0;
+                                }
+                            }
 #pragma unroll
                             for (int t = 0; t < T; ++t)
                             {
@@ -708,7 +732,7 @@ __global__ void __launch_bounds__(march_threads(N), N <= 36 ? 2 : 1) sweep_march
             PBTE_STAMP(i0, 9);
             block(0, true, op);  // source / pseudo-time term: X = c1 T_old + c2 u_old (vectors 0 and 1 of the slot)
             for (int m = 0; m < nin; ++m)
-                if (interior >> m & 1u) block((size_t)(2 + m) * kTile * NS, false, op + (size_t)(1 + m) * FR);
+                if (interior >> m & 1u) block((size_t)(2 + m) * kTile * NS, false, op + (size_t)(1 + m) * OPS);
 #ifdef PBTE_TRACE
             if (acc[0][0][0] == 1.2345e300) PBTE_STAMP(i0, 15);  // the stamp below waits for the accumulators
 #endif
