@@ -134,6 +134,23 @@ def test_register_operator_variant_consistent_traces(name, monkeypatch):
     hc.close()
 
 
+def test_converged_solution_matches_oracle():
+    """Seconds-to-converged-T leg of the benchmark: with consistent face traces the source iteration converges; the CUDA path
+    and the oracle stop after the same number of iterations (reference stop test, tol 1e-8) with the same fields."""
+    hc = host_case("c2_hex_p2_small", face_rule=1)
+    P = hc.problem
+    want = orc.solve(P, 3000, 1e-8, cache_lu=True, threads=8)
+    s = pb.Solver(P, kernel=0)
+    s.build_schedule()
+    it, res, hist = s.solve(3000, 1e-8)
+    got = s.download_moments()
+    assert 1 < it < 3000 and res < 1e-8
+    assert it == want["iters"]
+    assert rel(got["Tc"], want["Tc"]) <= 1e-9 and rel(got["Qc"], want["Qc"]) <= 1e-9
+    s.close()
+    hc.close()
+
+
 def test_marching_kernel_on_refined_simplex_mesh():
     """Refined tetrahedra: 30 operator classes, 28 upwind DAGs, half-empty tiles; compared with the per-element LU kernel
     (the oracle needs minutes here) at 1e-10 after 3 iterations."""
