@@ -40,6 +40,8 @@ SAMPLE = dict(WORKLOAD, refine=1)  # CPU legs: same workload one refinement leve
 EXTRA_WORKLOADS = {
     "c3": dict(mesh="unit-cube-tet", order=2, refine=3, angle_dim=3, polar=8, azimuth=16, num_spectral=20,
                label="C3: builtin unit-cube-tet refine 3 (196608 tets), DG order 2 (ndof 10), 8 x 16 = 128 directions, non-gray Si = 40 bands"),
+    "c5": dict(mesh="unit-square-quad", order=4, refine=5, angle_dim=2, polar=1, azimuth=64, num_spectral=20, bcs={1: -0.5, 2: -0.5, 3: 0.5, 4: -0.5},
+               label="C5: builtin unit-square-quad refine 5 (65536 quads), DG order 4 (ndof 25), 64 azimuth directions (2-D), non-gray Si = 40 bands"),
     "c4": dict(mesh="unit-cube-hex", order=3, refine=2, angle_dim=3, polar=16, azimuth=32, num_spectral=20,
                label="C4 (1-GPU strong-scaling point of SURVEY 8d): unit-cube-hex refine 2 (4096 hexes), DG order 3 (ndof 64), 16 x 32 = 512 directions, 40 bands"),
 }
@@ -276,7 +278,7 @@ def run_gpu(args, rank, world, local_rank):
     wl = EXTRA_WORKLOADS.get(args.workload, WORKLOAD)
     strong = args.workload in EXTRA_WORKLOADS
     azim = wl["azimuth"] * (1 if strong else world)
-    hc = pb.HostCase(wl["mesh"], wl["order"], wl["refine"], wl["angle_dim"], wl["polar"], azim, True, False, BC3, num_spectral=wl["num_spectral"])
+    hc = pb.HostCase(wl["mesh"], wl["order"], wl["refine"], wl["angle_dim"], wl["polar"], azim, True, False, wl.get("bcs", BC3), num_spectral=wl["num_spectral"])
     P = hc.problem
     k0, k1 = pb.partition_directions(P.ndir, world, rank)
     stream = torch.cuda.Stream(device=local_rank)
@@ -513,7 +515,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2"] + sorted(EXTRA_WORKLOADS), help="c2 = the benchmark; c3/c4 = extra full-size measurements")
+    ap.add_argument("--workload", default="c2", choices=["c2"] + sorted(EXTRA_WORKLOADS), help="c2 = the benchmark; c3/c4/c5 = extra full-size measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-general", action="store_true", help="skip the side measurement of the per-element LU kernel")
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 warp-register, 3 shared-operator marching")
