@@ -7,11 +7,14 @@
 // built once per (class, slot) by build_operators_kernel (pivoted LU, same assembly as the per-element kernels).
 //
 // sweep_march_kernel: one CTA per slot (direction, band).  The CTA stages the slot's operators in shared memory with
-// one TMA bulk copy, then marches through the wavefront levels of its upwind DAG: a warp takes one tile of 8 elements of
-// one operator class and evaluates  U_tile(8 x n) = X(8 x n) P^T + sum_f Unbr_f(8 x n) Q_f^T  as FP64 tensor-core MMAs
-// (mma.sync m8n8k4: A fragment = element data straight from the flux, B fragment = operator in fragment order from shared
-// memory, accumulators in registers), adds the wall terms and writes the tile back in place.  Levels are separated by a
-// CTA barrier only: no inter-CTA dependency exists, one launch per sweep.
+// one TMA bulk copy (or, for meshes with many operator classes, reads them compactly stored through L1), then marches through
+// the tile sequence of its upwind DAG: producer warps gather a tile's element data into a shared-memory ring with cp.async,
+// a consumer warp takes one tile of 8 elements of one operator class and evaluates
+//     U_tile(8 x n) = X(8 x n) P^T + sum_f Unbr_f(8 x n) Q_f^T
+// as FP64 tensor-core MMAs (mma.sync m8n8k4: A fragment = element data from the ring, B fragment = operator, accumulators in
+// registers), adds the wall terms, writes the tile back in place and publishes it.  A tile starts once every tile up to its last
+// prerequisite is published (no level barrier); no inter-CTA dependency exists, one launch per sweep.
+// sweep_regop.cuh holds the variant that keeps the operators in registers (one operator class, large elements).
 // moments_from_flux_kernel then forms [Tc | Qc] by one coalesced streaming pass over the flux (fixed summation order).
 #pragma once
 
