@@ -11,6 +11,16 @@ namespace pbte_dev
 {
 constexpr int kMaxFaces = PBTE_MAX_FACES;
 constexpr int kMaxDim = 3;
+constexpr int kHistRing = 1024;  // entries of the iteration history ring (pinned host memory written by the device)
+
+// Iteration control in device memory: the finish step of an iteration compares the residual with `tol` and raises `stop`;
+// every kernel of a later iteration returns at once when it finds `stop` set (csrc/tail.cuh).
+struct DevCtrl
+{
+    double tol;    // stop when residual < tol (0: never)
+    int32_t stop;  // raised by the finish step of the first iteration with residual < tol
+    int32_t iter;  // finished iterations since the last reset
+};
 
 // Device image of the problem plus the sweep state, passed by value to the kernels.
 //
@@ -45,6 +55,7 @@ struct DevProblem
     const uint8_t *cls_in;          // [nclass][ne] interior faces with n.Omega < 0 for some direction of the class
     uint8_t *pivots;                // [nslots][ne][ndof] cached pivot lanes (FullLU policy) or nullptr
     int32_t *error_flag;            // device int: first PBTE_ERR_* raised by a kernel
+    const int32_t *stop;            // DevCtrl::stop: sweep and tail kernels return at once when it is set
 };
 
 // n . Omega with the reference's operation order: sequential sum over d < dim, no FMA contraction

@@ -11,6 +11,9 @@
 #include "sweep_regop.cuh"
 #include "sweep_shared.cuh"
 #include "sweep_warp.cuh"
+#include "tail.cuh"
+
+#include <nccl.h>
 
 #include <algorithm>
 #include <cmath>
@@ -116,7 +119,6 @@ struct pbte_handle
     int march_ring = 0, march_nv = 0;  // tile-ring slots per CTA, staged vectors per slot
     bool march_compact = false;        // operators stored compact (row-major n x n) instead of in MMA fragment order
     int march_op_stride = 0;           // doubles per operator in m_ops
-    int mom_chunks = 1;  // slot chunks of the moment pass
     size_t march_smem = 0;
     DevBuf<int32_t> m_slot_class, m_cls_level_begin, m_level_tile_begin, m_tile_oclass, m_tile_desc, m_cls_op_off, m_cls_op_cnt, m_oc_rep,
         m_oc_ksrc, m_oc_gsrc, m_cnbr;
@@ -125,15 +127,28 @@ struct pbte_handle
     DevBuf<double> m_ops, m_oph, m_ctbc;
 
     // state
-    DevBuf<double> flux, tc_prev, tv_prev, partial, mom, cell, norms, scratch, block_part;
+    DevBuf<double> flux, tc_prev, tv_prev, partial, mom, mom_part, cell, norms, scratch, block_part;
     DevBuf<int32_t> error_flag;
     double *h_norms = nullptr;  // pinned [4]
     int32_t *h_flag = nullptr;  // pinned
     double last_tv_norm = 0.0, last_tc_norm = 0.0;
 
-    // graph replay of one sweep
-    cudaGraphExec_t graph_exec = nullptr;
-    int graph_mode = -1;
+    // iteration control (csrc/tail.cuh): device-side stop test, history ring in pinned host memory mapped into the device
+    DevBuf<DevCtrl> ctrl;
+    DevBuf<unsigned> tickets;
+    double *h_hist = nullptr, *d_hist = nullptr;  // [kHistRing][4] = d2, t2, c2, error flag of every finished iteration
+    int64_t iter_enq = 0;                         // finish steps enqueued since the device counter was last reset
+    int tail_blocks = 0, tail_chunks = 1;         // grid of the tail kernels
+    static constexpr int kLookMax = 16;
+    cudaEvent_t ev_iter[kLookMax] = {};           // one event per in-flight iteration of pbte_cuda_solve
+
+    // communication: one all-reduce of [Tc | Qc] per iteration, issued by the library when a communicator is attached
+    ncclComm_t comm = nullptr;
+    int comm_rank = 0, comm_size = 1;
+
+    // graph replay of one sweep: [0] sweep + partial moments (the caller or NCCL reduces), [1] sweep + fused finish
+    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
+    int graph_mode[2] = {-1, -1};
 
     // stats
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
@@ -142,9 +157,23 @@ struct pbte_handle
     double last_sweep_ms = 0.0, last_finish_ms = 0.0, last_march_ms = 0.0;
     cudaEvent_t ev_march = nullptr;  // recorded right after the marching kernel (an event-record node when the sweep is a graph)
 
+    void drop_graphs()
+    {
+        for (int g = 0; g < 2; ++g)
+        {
+            if (graph_exec[g]) cudaGraphExecDestroy(graph_exec[g]);
+            graph_exec[g] = nullptr;
+            graph_mode[g] = -1;
+        }
+    }
+
     ~pbte_handle()
     {
-        if (graph_exec) cudaGraphExecDestroy(graph_exec);
+        drop_graphs();
+        if (comm) ncclCommDestroy(comm);
+        for (cudaEvent_t e : ev_iter)
+            if (e) cudaEventDestroy(e);
+        if (h_hist) cudaFreeHost(h_hist);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (ev2) cudaEventDestroy(ev2);
@@ -233,6 +262,7 @@ DevProblem make_dev_problem(pbte_handle *h)
     P.cls_in = h->cls_in.p;
     P.pivots = h->pivots.p;
     P.error_flag = h->error_flag.p;
+    P.stop = h->ctrl.p ? &h->ctrl.p->stop : nullptr;
     return P;
 }
 
@@ -373,11 +403,57 @@ int check_handle(pbte_handle *h)
     return PBTE_OK;
 }
 
-// Enqueue the kernels of one sweep on the handle's stream.  piv: 0 search, 1 search+record, 2 replay.
-int enqueue_sweep(pbte_handle *h, int piv, int64_t *launch_count)
+// Launch description of a tail kernel (csrc/tail.cuh).  nparts / per: see DevTail; finish: go on to the end of the iteration;
+// the sums go to mom_part when a communicator is attached and the finish does not follow at once (NCCL reduces mom_part -> mom).
+DevTail make_tail(pbte_handle *h, int nparts, int per, bool finish)
+{
+    DevTail Z{};
+    Z.nparts = nparts;
+    Z.slots_per_chunk = per;
+    Z.finish = finish ? 1 : 0;
+    Z.part = h->partial.p;
+    Z.mom = (!finish && h->comm) ? h->mom_part.p : h->mom.p;
+    Z.tickets = h->tickets.p;
+    Z.basis = h->basis.p;
+    Z.cell = h->cell.p;
+    Z.tv_prev = h->tv_prev.p;
+    Z.tc_prev = h->tc_prev.p;
+    Z.block_part = h->block_part.p;
+    Z.ctrl = h->ctrl.p;
+    Z.hist = h->d_hist;
+    return Z;
+}
+
+// The finish step on its own (after the caller's or NCCL's all-reduce of the moment vector).
+int enqueue_finish(pbte_handle *h)
+{
+    const DevProblem P = make_dev_problem(h);
+    iteration_tail_kernel<false><<<h->tail_blocks, kTailThreads, 0, h->stream>>>(P, make_tail(h, 0, 0, true));
+    ++h->launches;
+    CK(cudaGetLastError());
+    return PBTE_OK;
+}
+
+// Enqueue the kernels of one sweep on the handle's stream.  piv: 0 search, 1 search+record, 2 replay.  fuse: the tail kernel goes
+// on to the finish step (single-GPU iteration: the whole iteration tail is one launch).
+int enqueue_sweep(pbte_handle *h, int piv, bool fuse, int64_t *launch_count)
 {
     const DevProblem P = make_dev_problem(h);
     int64_t launches = 0;
+    if (h->nslots() == 0 || h->max_levels == 0)
+    {
+        // a rank without directions contributes zeros
+        double *dst = (!fuse && h->comm) ? h->mom_part.p : h->mom.p;
+        CK(cudaMemsetAsync(dst, 0, h->mom.count * sizeof(double), h->stream));
+        if (fuse)
+        {
+            iteration_tail_kernel<false><<<h->tail_blocks, kTailThreads, 0, h->stream>>>(P, make_tail(h, 0, 0, true));
+            ++launches;
+            CK(cudaGetLastError());
+        }
+        if (launch_count) *launch_count = launches;
+        return PBTE_OK;
+    }
     if (h->kernel_used == 3)
     {
         // one marching CTA per slot, then one streaming pass for the moments
@@ -422,12 +498,11 @@ int enqueue_sweep(pbte_handle *h, int piv, int64_t *launch_count)
             CK(cudaStreamIsCapturing(h->stream, &cs));
             CK(cudaEventRecordWithFlags(h->ev_march, h->stream, cs == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault));
         }
-        const size_t block = (size_t)h->ne * h->n, count = (size_t)(1 + h->dim) * block;
-        const int chunks = h->mom_chunks, per = (h->nslots() + chunks - 1) / chunks;
-        moments_from_flux_kernel<<<dim3((unsigned)((block + 255) / 256), (unsigned)chunks), 256, 0, h->stream>>>(P, chunks > 1 ? h->partial.p : h->mom.p, per);
-        if (chunks > 1) reduce_partials_kernel<<<(unsigned)((count + 255) / 256), 256, 0, h->stream>>>(count, chunks, h->partial.p, h->mom.p);
+        // [Tc | Qc] by one streaming pass over the flux; its last CTAs finish the iteration when `fuse`
+        const int chunks = h->tail_chunks, per = (h->nslots() + chunks - 1) / chunks;
+        iteration_tail_kernel<true><<<dim3((unsigned)h->tail_blocks, (unsigned)chunks), kTailThreads, 0, h->stream>>>(P, make_tail(h, chunks, per, fuse));
         CK(cudaGetLastError());
-        if (launch_count) *launch_count = chunks > 1 ? 3 : 2;
+        if (launch_count) *launch_count = 2;
         return PBTE_OK;
     }
     if (h->kernel_used == 2)
@@ -453,8 +528,8 @@ int enqueue_sweep(pbte_handle *h, int piv, int64_t *launch_count)
             ++launches;
         }
     }
-    const size_t count = (size_t)(1 + h->dim) * h->ne * h->n;
-    reduce_partials_kernel<<<(unsigned)((count + 255) / 256), 256, 0, h->stream>>>(count, h->nclass, h->partial.p, h->mom.p);
+    // class partials -> moment vector (ascending class order), then the finish step when `fuse`
+    iteration_tail_kernel<false><<<h->tail_blocks, kTailThreads, 0, h->stream>>>(P, make_tail(h, h->nclass, 0, fuse));
     ++launches;
     CK(cudaGetLastError());
     if (launch_count) *launch_count = launches;
@@ -648,13 +723,12 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
         CK(cudaMemsetAsync(h->error_flag.p, 0, sizeof(int32_t), h->stream));
         return fail(flag, "singular local system while building the shared operators");
     }
-    // moment pass: enough slot chunks that ~400k threads stream the flux (8 loads in flight each)
+    // tail pass: enough slot chunks that the streaming CTAs fill the machine several times over
     {
-        const size_t block = (size_t)h->ne * n;
-        int chunks = (int)std::min<size_t>((400000 + block - 1) / block, (size_t)std::max(1, ns / 16));
-        chunks = std::max(1, std::min(chunks, 64));
-        h->mom_chunks = chunks;
-        if ((size_t)chunks > (size_t)nclass) CK(h->partial.alloc((size_t)chunks * (1 + h->dim) * block));
+        int chunks = (12 * 148 + h->tail_blocks - 1) / std::max(1, h->tail_blocks);
+        chunks = std::max(1, std::min(chunks, std::min(64, std::max(1, ns / 8))));
+        if (const char *ev = std::getenv("PBTE_TAIL_CHUNKS")) chunks = std::max(1, std::min(std::atoi(ev), std::max(1, ns)));
+        h->tail_chunks = chunks;
     }
     *used = true;
     return PBTE_OK;
@@ -663,6 +737,7 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
 int alloc_moment_state(pbte_handle *h)
 {
     const size_t block = (size_t)h->ne * h->n, nm = 1 + h->dim;
+    if (h->np > 2 * kTailThreads) return fail(PBTE_ERR_INVALID, "ndof too large for the iteration tail kernel");
     CK(h->mom.alloc(nm * block));
     CK(h->cell.alloc(nm * h->ne));
     CK(h->tv_prev.alloc(h->ne));
@@ -674,7 +749,73 @@ int alloc_moment_state(pbte_handle *h)
     CK(cudaMemsetAsync(h->tv_prev.p, 0, h->ne * sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->tc_prev.p, 0, h->tc_prev.count * sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->error_flag.p, 0, sizeof(int32_t), h->stream));
+    // tail kernels: a CTA owns 256 / (np/2) whole elements
+    const int epb = kTailThreads / (h->np / 2);
+    h->tail_blocks = (h->ne + epb - 1) / epb;
+    CK(h->tickets.alloc((size_t)h->tail_blocks + 1));
+    CK(cudaMemsetAsync(h->tickets.p, 0, h->tickets.count * sizeof(unsigned), h->stream));
+    CK(h->block_part.alloc((size_t)h->tail_blocks * 3));
+    CK(h->ctrl.alloc(1));
+    CK(cudaMemsetAsync(h->ctrl.p, 0, sizeof(DevCtrl), h->stream));
+    CK(cudaHostAlloc(&h->h_hist, sizeof(double) * 4 * kHistRing, cudaHostAllocMapped));
+    std::memset(h->h_hist, 0, sizeof(double) * 4 * kHistRing);
+    CK(cudaHostGetDevicePointer(&h->d_hist, h->h_hist, 0));
+    for (cudaEvent_t &e : h->ev_iter) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     return PBTE_OK;
+}
+
+// device-side iteration control: tolerance of the stop test, stop flag and iteration counter (all reset together)
+int reset_ctrl(pbte_handle *h, double tol)
+{
+    if (!h->ctrl.p) return PBTE_OK;
+    const DevCtrl c{tol, 0, 0};
+    CK(cudaMemcpyAsync(h->ctrl.p, &c, sizeof(c), cudaMemcpyHostToDevice, h->stream));  // pageable source: staged before the call returns
+    h->iter_enq = 0;
+    return PBTE_OK;
+}
+
+// One whole source iteration, enqueued: sweep, all-reduce of [Tc | Qc] when a communicator is attached, finish.  No host
+// synchronisation; the iteration's history entry becomes valid when the stream reaches the end of the finish step.
+int graph_sweep(pbte_handle *h, bool fuse);
+int enqueue_iteration(pbte_handle *h)
+{
+    int st;
+    if (!h->comm) return graph_sweep(h, true);
+    if ((st = graph_sweep(h, false))) return st;
+    const ncclResult_t r = ncclAllReduce(h->mom_part.p, h->mom.p, h->mom.count, ncclDouble, ncclSum, h->comm, h->stream);
+    if (r != ncclSuccess) return fail(PBTE_ERR_CUDA, std::string("ncclAllReduce: ") + ncclGetErrorString(r));
+    return enqueue_finish(h);
+}
+
+// Waits for history entry `index` (an event recorded behind its finish step) and decodes it.
+int read_history(pbte_handle *h, int64_t index, cudaEvent_t ev, double *residual)
+{
+    if (ev) CK(cudaEventSynchronize(ev));
+    else CK(cudaStreamSynchronize(h->stream));
+    const volatile double *e = h->h_hist + (size_t)(index % kHistRing) * 4;
+    const double d2 = e[0], t2 = e[1], c2 = e[2];
+    const int flag = (int)e[3];
+    h->last_tv_norm = std::sqrt(t2);
+    h->last_tc_norm = std::sqrt(c2);
+    if (flag != 0)
+    {
+        cudaMemsetAsync(h->error_flag.p, 0, sizeof(int32_t), h->stream);
+        return fail(flag, "a sweep kernel reported a singular local system");
+    }
+    if (!(t2 > 0.0)) return fail(PBTE_ERR_ZERO_NORM, "Tv norm is zero; cannot compute residual.");
+    if (residual) *residual = std::sqrt(d2) / std::sqrt(t2);
+    return PBTE_OK;
+}
+
+void read_timers(pbte_handle *h)
+{
+    if (!h->sweep_timed) return;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_sweep_ms = ms;
+    if (h->kernel_used == 3 && cudaEventElapsedTime(&ms, h->ev0, h->ev_march) == cudaSuccess) h->last_march_ms = ms;
+    else h->last_march_ms = 0.0;
+    if (cudaEventElapsedTime(&ms, h->ev1, h->ev2) == cudaSuccess) h->last_finish_ms = ms;
+    (void)cudaGetLastError();
 }
 }  // namespace
 
@@ -864,12 +1005,7 @@ int pbte_cuda_build_schedule(pbte_handle_t *h)
     DeviceGuard guard(h->device);
     const int ne = h->ne, F = h->F, nloc = h->nloc();
     h->scheduled = false;
-    if (h->graph_exec)
-    {
-        cudaGraphExecDestroy(h->graph_exec);
-        h->graph_exec = nullptr;
-        h->graph_mode = -1;
-    }
+    h->drop_graphs();
     if (nloc == 0 || ne == 0)
     {
         h->nclass = 0;
@@ -1026,8 +1162,6 @@ int pbte_cuda_build_schedule(pbte_handle_t *h)
         if ((st = upload(h->slot_qf, sqf.data(), sqf.size(), h->stream))) return st;
         CK(cudaStreamSynchronize(h->stream));
 
-        CK(h->partial.alloc((size_t)nclass * (1 + h->dim) * ne * h->n));
-
         // kernel choice and its shared-memory shape
         int nF = 0, nK = 0;
         for (size_t i = 0; i < cin.size(); ++i)
@@ -1065,6 +1199,17 @@ int pbte_cuda_build_schedule(pbte_handle_t *h)
             bool used = false;
             if ((st = setup_march(h, cin, cbin, &used))) return st;
             if (used) h->kernel_used = 3;
+        }
+        // partial moment vectors: one per slot chunk of the tail pass (marching path) or one per upwind-DAG class (per-element kernels)
+        {
+            const size_t vec = (size_t)(1 + h->dim) * ne * h->n;
+            if (h->kernel_used == 3)
+            {
+                if (h->tail_chunks > 1) CK(h->partial.alloc((size_t)h->tail_chunks * vec));
+                else h->partial.release();
+                h->items.release();  // the level lists of (class, element) items drive the per-element kernels only
+            }
+            else CK(h->partial.alloc((size_t)nclass * vec));
         }
         h->pivots.release();
         h->pivots_recorded = false;
@@ -1218,14 +1363,22 @@ int pbte_cuda_download_moments(pbte_handle_t *h, double *Tc, double *Qc, double 
 }
 
 // -------------------------------------------------------------------------------------------------
-int pbte_cuda_sweep(pbte_handle_t *h)
+}  // extern "C"
+
+namespace
 {
-    int st = check_handle(h);
-    if (st) return st;
+int check_sweep_ready(pbte_handle *h)
+{
     if (!h->has_matrices || !h->has_bands) return fail(PBTE_ERR_STATE, "sweep needs the full problem image");
     if (!h->scheduled) return fail(PBTE_ERR_STATE, "sweep before build_schedule");
     if (h->missing_bc) return fail(PBTE_ERR_MISSING_BC, "a boundary face has no isothermal wall temperature");
-    DeviceGuard guard(h->device);
+    return PBTE_OK;
+}
+
+// One sweep (and its tail) on the handle's stream, replayed as a CUDA graph where possible.
+int graph_sweep(pbte_handle *h, bool fuse)
+{
+    int st;
     int piv = 0;
     if (h->pivots.p) piv = h->pivots_recorded ? 2 : 1;
     CK(cudaEventRecord(h->ev0, h->stream));
@@ -1234,42 +1387,167 @@ int pbte_cuda_sweep(pbte_handle_t *h)
 #ifdef PBTE_TRACE
     if (std::getenv("PBTE_TRACE_FILE")) graph_ok = false;  // the traced sweep synchronises and writes a file
 #endif
-    if (graph_ok)
+    const int g = fuse ? 1 : 0;
+    if (graph_ok && (!h->graph_exec[g] || h->graph_mode[g] != piv))
     {
-        if (!h->graph_exec || h->graph_mode != piv)
+        if (h->graph_exec[g])
         {
-            if (h->graph_exec)
-            {
-                cudaGraphExecDestroy(h->graph_exec);
-                h->graph_exec = nullptr;
-            }
-            cudaGraph_t graph = nullptr;
-            CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-            st = enqueue_sweep(h, piv, &launches);
-            const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
-            if (st) return st;
-            if (ce != cudaSuccess) return fail(PBTE_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
-            CK(cudaGraphInstantiate(&h->graph_exec, graph, 0));
-            cudaGraphDestroy(graph);
-            h->graph_mode = piv;
+            cudaGraphExecDestroy(h->graph_exec[g]);
+            h->graph_exec[g] = nullptr;
+        }
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        st = enqueue_sweep(h, piv, fuse, &launches);
+        const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+        cudaError_t ie = cudaSuccess;
+        if (st == PBTE_OK && ce == cudaSuccess) ie = cudaGraphInstantiate(&h->graph_exec[g], graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (st != PBTE_OK || ce != cudaSuccess || ie != cudaSuccess)
+        {
+            // capture or instantiation failed: this handle goes on with plain launches
+            (void)cudaGetLastError();
+            h->graph_exec[g] = nullptr;
+            h->use_graph = 0;
+            graph_ok = false;
+        }
+        else
+        {
+            h->graph_mode[g] = piv;
             h->launches_per_sweep = launches;
             // the capture consumed the event record: re-record on the live stream
             CK(cudaEventRecord(h->ev0, h->stream));
         }
-        CK(cudaGraphLaunch(h->graph_exec, h->stream));
+    }
+    if (graph_ok)
+    {
+        CK(cudaGraphLaunch(h->graph_exec[g], h->stream));
         launches = h->launches_per_sweep;
     }
     else
     {
-        if ((st = enqueue_sweep(h, piv, &launches))) return st;
+        if ((st = enqueue_sweep(h, piv, fuse, &launches))) return st;
         h->launches_per_sweep = launches;
     }
     CK(cudaEventRecord(h->ev1, h->stream));
+    if (fuse) CK(cudaEventRecord(h->ev2, h->stream));
     h->sweep_timed = true;
     h->launches += launches;
     ++h->sweeps;
+    if (fuse) ++h->iter_enq;
     if (piv == 1) h->pivots_recorded = true;
     return PBTE_OK;
+}
+
+// Source iteration over a set of handles that share one communicator set (or a single handle): up to `look` iterations are in
+// flight; the host reads the residual history behind them and stops enqueueing at the first residual below tol.  The device's
+// own stop test (csrc/tail.cuh) turns whatever was enqueued beyond that iteration into no-ops, so the state that comes back is
+// the one the reference leaves: that of the first iteration with res < tol (src/PBTESolver.cpp:313-330).
+int solve_handles(pbte_handle **hs, int nh, int32_t max_iter, double tol, int32_t *iters_done, double *residual, double *history,
+                  pbte_iteration_callback_t cb, void *user)
+{
+    int st = PBTE_OK;
+    for (int i = 0; i < nh; ++i)
+    {
+        if ((st = check_sweep_ready(hs[i]))) return st;
+        if (!hs[i]->has_basis) return fail(PBTE_ERR_STATE, "solve needs basis_integrals in the problem image");
+    }
+    int look = 4;
+    if (const char *ev = std::getenv("PBTE_LOOKAHEAD")) look = std::atoi(ev);
+    look = std::max(1, std::min(look, (int)pbte_handle::kLookMax));
+    for (int i = 0; i < nh; ++i)
+    {
+        DeviceGuard guard(hs[i]->device);
+        if ((st = reset_ctrl(hs[i], tol))) return st;
+    }
+    double res = 0.0;
+    int enq = 0, seen = 0;
+    while (seen < max_iter && st == PBTE_OK)
+    {
+        while (enq < max_iter && enq - seen < look && st == PBTE_OK)
+        {
+            // sweeps of all handles, then their all-reduces as one NCCL group, then the finish steps
+            if (nh > 1)
+            {
+                for (int i = 0; i < nh && st == PBTE_OK; ++i)
+                {
+                    DeviceGuard guard(hs[i]->device);
+                    st = graph_sweep(hs[i], false);
+                }
+                if (st) break;
+                ncclGroupStart();
+                ncclResult_t r = ncclSuccess;
+                for (int i = 0; i < nh && r == ncclSuccess; ++i)
+                    r = ncclAllReduce(hs[i]->mom_part.p, hs[i]->mom.p, hs[i]->mom.count, ncclDouble, ncclSum, hs[i]->comm, hs[i]->stream);
+                const ncclResult_t r2 = ncclGroupEnd();
+                if (r != ncclSuccess || r2 != ncclSuccess)
+                {
+                    st = fail(PBTE_ERR_CUDA, std::string("ncclAllReduce: ") + ncclGetErrorString(r != ncclSuccess ? r : r2));
+                    break;
+                }
+                for (int i = 0; i < nh && st == PBTE_OK; ++i)
+                {
+                    DeviceGuard guard(hs[i]->device);
+                    if ((st = enqueue_finish(hs[i]))) break;
+                    if (cudaEventRecord(hs[i]->ev2, hs[i]->stream) != cudaSuccess) st = fail(PBTE_ERR_CUDA, "cudaEventRecord failed");
+                    ++hs[i]->iter_enq;
+                }
+            }
+            else
+            {
+                DeviceGuard guard(hs[0]->device);
+                st = enqueue_iteration(hs[0]);
+                if (st == PBTE_OK && hs[0]->comm)
+                {
+                    if (cudaEventRecord(hs[0]->ev2, hs[0]->stream) != cudaSuccess) st = fail(PBTE_ERR_CUDA, "cudaEventRecord failed");
+                    ++hs[0]->iter_enq;
+                }
+            }
+            if (st) break;
+            {
+                DeviceGuard guard(hs[0]->device);
+                if (cudaEventRecord(hs[0]->ev_iter[enq % look], hs[0]->stream) != cudaSuccess) st = fail(PBTE_ERR_CUDA, "cudaEventRecord failed");
+            }
+            ++enq;
+        }
+        if (st) break;
+        {
+            // every handle computes the same residual from the same all-reduced vector: read it from the first one
+            DeviceGuard guard(hs[0]->device);
+            st = read_history(hs[0], seen, hs[0]->ev_iter[seen % look], &res);
+        }
+        if (st) break;
+        if (history) history[seen] = res;
+        if (cb) cb(user, seen + 1, res, hs[0]->last_tv_norm, hs[0]->last_tc_norm);
+        ++seen;
+        if (res < tol) break;
+    }
+    // drain (iterations enqueued beyond the stop are no-ops on the device) and leave the controls as they were
+    for (int i = 0; i < nh; ++i)
+    {
+        DeviceGuard guard(hs[i]->device);
+        cudaStreamSynchronize(hs[i]->stream);
+        read_timers(hs[i]);
+        hs[i]->last_tv_norm = hs[0]->last_tv_norm;
+        hs[i]->last_tc_norm = hs[0]->last_tc_norm;
+        const int st2 = reset_ctrl(hs[i], 0.0);
+        if (st == PBTE_OK) st = st2;
+        cudaStreamSynchronize(hs[i]->stream);
+    }
+    if (iters_done) *iters_done = seen;
+    if (residual) *residual = res;
+    return st;
+}
+}  // namespace
+
+extern "C" {
+
+int pbte_cuda_sweep(pbte_handle_t *h)
+{
+    int st = check_handle(h);
+    if (st) return st;
+    if ((st = check_sweep_ready(h))) return st;
+    DeviceGuard guard(h->device);
+    return graph_sweep(h, false);
 }
 
 int pbte_cuda_moment_buffer(pbte_handle_t *h, double **device_ptr, size_t *count)
@@ -1277,6 +1555,7 @@ int pbte_cuda_moment_buffer(pbte_handle_t *h, double **device_ptr, size_t *count
     int st = check_handle(h);
     if (st) return st;
     if (!h->mom.p) return fail(PBTE_ERR_STATE, "handle holds no moment state");
+    if (h->comm) return fail(PBTE_ERR_STATE, "a communicator is attached: the library all-reduces the moment vector itself");
     if (device_ptr) *device_ptr = h->mom.p;
     if (count) *count = h->mom.count;
     return PBTE_OK;
@@ -1288,50 +1567,46 @@ int pbte_cuda_finish_iteration(pbte_handle_t *h, double *residual)
     if (st) return st;
     if (!h->mom.p || !h->has_basis) return fail(PBTE_ERR_STATE, "finish_iteration needs basis_integrals in the problem image");
     DeviceGuard guard(h->device);
-    // cell integrals, norms of the stop test and the hand-over Tv_prev <- Tv, Tc_prev <- Tc (src/PBTESolver.cpp:313-329) in two launches
-    double d2 = 0, t2 = 0, c2 = 0;
+    if (h->comm)
     {
-        int seg = 1;
-        while (seg < h->n && seg < 32) seg <<= 1;
-        const size_t threads = (size_t)(1 + h->dim) * h->ne * seg;
-        const unsigned nblocks = (unsigned)((threads + 255) / 256);
-        if (h->block_part.count < (size_t)nblocks * 3) CK(h->block_part.alloc((size_t)nblocks * 3));
-        finish_cells_kernel<<<nblocks, 256, 0, h->stream>>>(h->ne, h->n, h->np, 1 + h->dim, seg, h->mom.p, h->basis.p, h->cell.p, h->tv_prev.p,
-                                                           h->tc_prev.p, h->block_part.p);
-        finish_norms_kernel<<<1, 256, 0, h->stream>>>((int)nblocks, h->block_part.p, h->norms.p);
-        h->launches += 2;
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(h->h_norms, h->norms.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaMemcpyAsync(h->h_flag, h->error_flag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        const ncclResult_t r = ncclAllReduce(h->mom_part.p, h->mom.p, h->mom.count, ncclDouble, ncclSum, h->comm, h->stream);
+        if (r != ncclSuccess) return fail(PBTE_ERR_CUDA, std::string("ncclAllReduce: ") + ncclGetErrorString(r));
     }
+    // cell integrals, norms of the stop test and the hand-over Tv_prev <- Tv, Tc_prev <- Tc (src/PBTESolver.cpp:313-329): one launch
+    if ((st = enqueue_finish(h))) return st;
     CK(cudaEventRecord(h->ev2, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    d2 = h->h_norms[0];
-    t2 = h->h_norms[1];
-    c2 = h->h_norms[2];
-    if (h->sweep_timed)
+    const int64_t index = h->iter_enq++;
+    st = read_history(h, index, nullptr, residual);
+    read_timers(h);
+    return st;
+}
+
+int pbte_cuda_iterate_async(pbte_handle_t *h)
+{
+    int st = check_handle(h);
+    if (st) return st;
+    if ((st = check_sweep_ready(h))) return st;
+    if (!h->has_basis) return fail(PBTE_ERR_STATE, "iterate needs basis_integrals in the problem image");
+    DeviceGuard guard(h->device);
+    if ((st = enqueue_iteration(h))) return st;
+    if (h->comm)
     {
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_sweep_ms = ms;
-        if (h->kernel_used == 3 && cudaEventElapsedTime(&ms, h->ev0, h->ev_march) == cudaSuccess) h->last_march_ms = ms;
-        else
-        {
-            h->last_march_ms = 0.0;
-            (void)cudaGetLastError();
-        }
-        if (cudaEventElapsedTime(&ms, h->ev1, h->ev2) == cudaSuccess) h->last_finish_ms = ms;
+        CK(cudaEventRecord(h->ev2, h->stream));
+        ++h->iter_enq;
     }
-    h->last_tv_norm = std::sqrt(t2);
-    h->last_tc_norm = std::sqrt(c2);
-    if (*h->h_flag != 0)
-    {
-        const int flag = *h->h_flag;
-        cudaMemsetAsync(h->error_flag.p, 0, sizeof(int32_t), h->stream);
-        return fail(flag, "a sweep kernel reported a singular local system");
-    }
-    if (!(t2 > 0.0)) return fail(PBTE_ERR_ZERO_NORM, "Tv norm is zero; cannot compute residual.");
-    if (residual) *residual = std::sqrt(d2) / std::sqrt(t2);
     return PBTE_OK;
+}
+
+int pbte_cuda_iterate_sync(pbte_handle_t *h, int64_t *iterations, double *residual)
+{
+    int st = check_handle(h);
+    if (st) return st;
+    DeviceGuard guard(h->device);
+    CK(cudaStreamSynchronize(h->stream));
+    read_timers(h);
+    if (iterations) *iterations = h->iter_enq;
+    if (h->iter_enq == 0) return PBTE_OK;
+    return read_history(h, h->iter_enq - 1, nullptr, residual);
 }
 
 int pbte_cuda_last_norms(pbte_handle_t *h, double *tv_norm, double *tc_fnorm)
@@ -1347,18 +1622,105 @@ int pbte_cuda_solve(pbte_handle_t *h, int32_t max_iter, double tol, int32_t *ite
 {
     int st = check_handle(h);
     if (st) return st;
-    double res = 0.0;
-    int it = 0;
-    for (; it < max_iter;)
+    return solve_handles(&h, 1, max_iter, tol, iters_done, residual, history, nullptr, nullptr);
+}
+
+int pbte_cuda_solve_ex(pbte_handle_t *const *handles, int32_t n_handles, int32_t max_iter, double tol, int32_t *iters_done, double *residual,
+                       double *history, pbte_iteration_callback_t on_iteration, void *user)
+{
+    if (!handles || n_handles < 1) return fail(PBTE_ERR_INVALID, "solve_ex: no handles");
+    std::vector<pbte_handle *> hs(handles, handles + n_handles);
+    for (pbte_handle *h : hs)
     {
-        if ((st = pbte_cuda_sweep(h))) return st;
-        if ((st = pbte_cuda_finish_iteration(h, &res))) return st;
-        if (history) history[it] = res;
-        ++it;
-        if (res < tol) break;
+        if (!h) return fail(PBTE_ERR_INVALID, "null handle");
+        if (n_handles > 1 && (!h->comm || h->comm_size != n_handles))
+            return fail(PBTE_ERR_STATE, "solve_ex over several handles needs pbte_cuda_comm_attach_all on exactly these handles");
     }
-    if (iters_done) *iters_done = it;
-    if (residual) *residual = res;
+    return solve_handles(hs.data(), n_handles, max_iter, tol, iters_done, residual, history, on_iteration, user);
+}
+
+// ---- communication -------------------------------------------------------------------------------
+int pbte_cuda_comm_get_unique_id(void *id)
+{
+    if (!id) return fail(PBTE_ERR_INVALID, "null id");
+    static_assert(sizeof(ncclUniqueId) == PBTE_COMM_ID_BYTES, "PBTE_COMM_ID_BYTES must match ncclUniqueId");
+    ncclUniqueId uid;
+    const ncclResult_t r = ncclGetUniqueId(&uid);
+    if (r != ncclSuccess) return fail(PBTE_ERR_CUDA, std::string("ncclGetUniqueId: ") + ncclGetErrorString(r));
+    std::memcpy(id, &uid, sizeof(uid));
+    return PBTE_OK;
+}
+
+static int after_attach(pbte_handle *h)
+{
+    h->drop_graphs();
+    CK(h->mom_part.alloc(h->mom.count));
+    CK(cudaMemsetAsync(h->mom_part.p, 0, h->mom.count * sizeof(double), h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return PBTE_OK;
+}
+
+int pbte_cuda_comm_attach(pbte_handle_t *h, const void *id, int32_t rank, int32_t world_size)
+{
+    int st = check_handle(h);
+    if (st) return st;
+    if (!id || world_size < 1 || rank < 0 || rank >= world_size) return fail(PBTE_ERR_INVALID, "comm_attach: bad rank / world size");
+    if (h->comm) return fail(PBTE_ERR_STATE, "a communicator is already attached");
+    if (!h->mom.p) return fail(PBTE_ERR_STATE, "handle holds no moment state");
+    DeviceGuard guard(h->device);
+    ncclUniqueId uid;
+    std::memcpy(&uid, id, sizeof(uid));
+    const ncclResult_t r = ncclCommInitRank(&h->comm, world_size, uid, rank);
+    if (r != ncclSuccess)
+    {
+        h->comm = nullptr;
+        return fail(PBTE_ERR_CUDA, std::string("ncclCommInitRank: ") + ncclGetErrorString(r));
+    }
+    h->comm_rank = rank;
+    h->comm_size = world_size;
+    return after_attach(h);
+}
+
+int pbte_cuda_comm_attach_all(pbte_handle_t *const *handles, int32_t n)
+{
+    if (!handles || n < 1) return fail(PBTE_ERR_INVALID, "comm_attach_all: no handles");
+    std::vector<int> devs(n);
+    for (int i = 0; i < n; ++i)
+    {
+        if (!handles[i] || !handles[i]->mom.p) return fail(PBTE_ERR_INVALID, "comm_attach_all: null handle or handle without moment state");
+        if (handles[i]->comm) return fail(PBTE_ERR_STATE, "a communicator is already attached");
+        if (handles[i]->mom.count != handles[0]->mom.count) return fail(PBTE_ERR_INVALID, "comm_attach_all: handles of different problems");
+        devs[i] = handles[i]->device;
+        for (int j = 0; j < i; ++j)
+            if (devs[j] == devs[i]) return fail(PBTE_ERR_INVALID, "comm_attach_all: two handles on one device (NCCL needs one device per rank)");
+    }
+    std::vector<ncclComm_t> comms(n, nullptr);
+    const ncclResult_t r = ncclCommInitAll(comms.data(), n, devs.data());
+    if (r != ncclSuccess) return fail(PBTE_ERR_CUDA, std::string("ncclCommInitAll: ") + ncclGetErrorString(r));
+    for (int i = 0; i < n; ++i)
+    {
+        handles[i]->comm = comms[i];
+        handles[i]->comm_rank = i;
+        handles[i]->comm_size = n;
+        DeviceGuard guard(handles[i]->device);
+        const int st = after_attach(handles[i]);
+        if (st) return st;
+    }
+    return PBTE_OK;
+}
+
+int pbte_cuda_comm_detach(pbte_handle_t *h)
+{
+    int st = check_handle(h);
+    if (st) return st;
+    DeviceGuard guard(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->comm) ncclCommDestroy(h->comm);
+    h->comm = nullptr;
+    h->comm_rank = 0;
+    h->comm_size = 1;
+    h->mom_part.release();
+    h->drop_graphs();
     return PBTE_OK;
 }
 

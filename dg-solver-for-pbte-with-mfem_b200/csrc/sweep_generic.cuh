@@ -12,6 +12,7 @@ namespace pbte_dev
 __global__ void __launch_bounds__(128) sweep_generic_kernel(DevProblem P, const int2 *__restrict__ items, int item_begin)
 {
     extern __shared__ double sm[];
+    if (*P.stop) return;  // the iteration before this one met the stop test (csrc/tail.cuh)
     const int n = P.n, F = P.F, dim = P.dim, T = blockDim.x, t = threadIdx.x;
     double *A = sm;
     double *b = A + (size_t)n * n;

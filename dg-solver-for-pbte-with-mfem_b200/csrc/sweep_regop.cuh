@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(regop_threads(N), regop_ctas(N)) sweep_march_r
     constexpr int CH = NP / 2;                      // 16-byte chunks per row
     static_assert(CW <= 32, "one lane of a neighbour producer polls one consumer warp");
     extern __shared__ __align__(128) unsigned char sm_raw[];
+    if (*P.stop) return;  // the iteration before this one met the stop test (csrc/tail.cuh)
     const int s = blockIdx.x;
     const int c = S.slot_class[s];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -15,7 +15,7 @@
 // registers), adds the wall terms, writes the tile back in place and publishes it.  A tile starts once every tile up to its last
 // prerequisite is published (no level barrier); no inter-CTA dependency exists, one launch per sweep.
 // sweep_regop.cuh holds the variant that keeps the operators in registers (one operator class, large elements).
-// moments_from_flux_kernel then forms [Tc | Qc] by one coalesced streaming pass over the flux (fixed summation order).
+// iteration_tail_kernel (tail.cuh) then forms [Tc | Qc] by one streaming pass over the flux and finishes the iteration.
 #pragma once
 
 #include "common.cuh"
@@ -446,6 +446,7 @@ __global__ void __launch_bounds__(march_threads(N), N <= 36 ? 2 : 1) sweep_march
     constexpr int CH = NP / 2;              // 16-byte chunks per row
     extern __shared__ __align__(128) unsigned char sm_raw[];
     __shared__ __align__(8) uint64_t s_bar;
+    if (*P.stop) return;  // the iteration before this one met the stop test (csrc/tail.cuh)
     const int s = blockIdx.x;
     const int c = S.slot_class[s];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -833,49 +834,6 @@ __global__ void __launch_bounds__(march_threads(N), N <= 36 ? 2 : 1) sweep_march
             }
         }
     }
-}
-
-// out[y][m][x] = sum_{s in slot chunk y} fac_m[s] * flux[s][x], x = (element, dof) flattened; slots in ascending order.
-// grid (ceil(ne*n / 256), chunks): the slot range is cut into gridDim.y chunks so that enough loads are in flight to fill
-// HBM; the chunk partials are summed in ascending order by reduce_partials_kernel (fixed summation order: bit-reproducible).
-__global__ void __launch_bounds__(256) moments_from_flux_kernel(DevProblem P, double *__restrict__ out, int slots_per_chunk)
-{
-    const size_t block = (size_t)P.ne * P.n;
-    const size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (x >= block) return;
-    const int dim = P.dim;
-    const int s_begin = blockIdx.y * slots_per_chunk, s_end = min(P.nslots, s_begin + slots_per_chunk);
-    double t = 0.0, q0 = 0.0, q1 = 0.0, q2 = 0.0;
-    const size_t e = x / P.n, sblock = (size_t)P.ne * P.np;  // flux rows are padded to np doubles
-    const double *u = P.flux + e * P.np + (x - e * P.n);
-    int s = s_begin;
-    for (; s + 8 <= s_end; s += 8)
-    {
-        double v[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = __ldcs(u + (size_t)(s + k) * sblock);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-        {
-            t = fma(P.slot_mf[s + k], v[k], t);
-            q0 = fma(P.slot_qf[3 * (s + k)], v[k], q0);
-            q1 = fma(P.slot_qf[3 * (s + k) + 1], v[k], q1);
-            q2 = fma(P.slot_qf[3 * (s + k) + 2], v[k], q2);
-        }
-    }
-    for (; s < s_end; ++s)
-    {
-        const double v = __ldcs(u + (size_t)s * sblock);
-        t = fma(P.slot_mf[s], v, t);
-        q0 = fma(P.slot_qf[3 * s], v, q0);
-        q1 = fma(P.slot_qf[3 * s + 1], v, q1);
-        q2 = fma(P.slot_qf[3 * s + 2], v, q2);
-    }
-    double *mom = out + (size_t)blockIdx.y * (1 + dim) * block;
-    mom[x] = t;
-    mom[block + x] = q0;
-    if (dim > 1) mom[2 * block + x] = q1;
-    if (dim > 2) mom[3 * block + x] = q2;
 }
 
 }  // namespace pbte_dev

@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sweep_warp_kernel(DevProble
     constexpr int NN = N * N;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ double sm[];
+    if (*P.stop) return;  // the iteration before this one met the stop test (csrc/tail.cuh)
     const int F = P.F;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int2 it = items[item_begin + blockIdx.x];

@@ -1,0 +1,265 @@
+// End of a source iteration in (at most) two launches, and in ONE on a single GPU:
+//
+//   iteration_tail_kernel<true>   streams the flux once ([Tc | Qc] partial sums per slot chunk, MacroscopicQuantities::
+//                                 AccumulateDirectionalCoeff, src/MacroscopicQuantities.cpp:104-128); the LAST chunk CTA of an
+//                                 element block adds the chunk partials in ascending order (fixed order: bit-reproducible) and,
+//                                 when no all-reduce has to happen in between (finish = 1), goes straight on to
+//   the finish step               cell integrals Tv, Qv (::Finalize :130-157), the three squared norms of the stop test
+//                                 (::Residual :159-166 and the two norms the reference prints), the hand-over tc_prev <- Tc,
+//                                 tv_prev <- Tv (src/PBTESolver.cpp:328-329); the LAST block of the grid adds the block
+//                                 partials in a fixed order, writes {d2, t2, c2, error flag} into the iteration history (pinned
+//                                 host memory mapped into the device), advances the iteration counter and raises the STOP flag
+//                                 when residual < tol: every kernel of a later iteration returns at once then, so the host may
+//                                 enqueue iterations ahead of the residuals it has seen (no synchronisation between iterations)
+//                                 and the result is still the reference's: the state of the first iteration with res < tol.
+//   iteration_tail_kernel<false>  the same without the streaming pass: sums `nparts` partial vectors that a sweep kernel wrote
+//                                 (the per-element kernels write one per upwind-DAG class) or takes the moment vector as it
+//                                 is (nparts = 0: after the all-reduce of a multi-GPU iteration), then finishes.
+//
+// Thread map: a CTA owns EPB = 256 / (np/2) whole elements; a thread owns one 16-byte chunk (two dofs) of one element row, so
+// the flux is read with 16-byte loads, 8 slots in flight per thread.
+#pragma once
+
+#include "common.cuh"
+
+namespace pbte_dev
+{
+constexpr int kTailThreads = 256;
+constexpr int kTailMaxVals = 512;  // EPB * n <= (256 / ch2) * 2 * ch2
+
+struct DevTail
+{
+    int nparts;            // STREAM: slot chunks (gridDim.y); else partial vectors to add (0: `mom` already holds the sums)
+    int slots_per_chunk;   // STREAM only
+    int finish;            // 1: go on to cell integrals / norms / hand-over
+    double *part;          // [nparts][1+dim][ne*n] partial sums (unused when nparts <= 1 && STREAM, or nparts == 0)
+    double *mom;           // [1+dim][ne*n] result of the reduction (the vector a multi-GPU iteration all-reduces)
+    unsigned *tickets;     // [gridDim.x + 1] arrival counters (zero between launches)
+    const double *basis;   // [ne][n]
+    double *cell;          // [1+dim][ne]  Tv | Qv
+    double *tv_prev;       // [ne]
+    double *tc_prev;       // [ne][np]
+    double *block_part;    // [gridDim.x][3]
+    DevCtrl *ctrl;
+    double *hist;          // device view of the pinned history ring [kHistRing][4]
+};
+
+__device__ __forceinline__ bool last_arrival(unsigned *ticket, unsigned expected, int *s_flag)
+{
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        const unsigned t = atomicAdd(ticket, 1u);
+        *s_flag = (t == expected - 1) ? 1 : 0;
+        if (t == expected - 1) *ticket = 0u;  // ready for the next launch
+    }
+    __syncthreads();
+    const bool last = *s_flag != 0;
+    if (last) __threadfence();
+    return last;
+}
+
+template <bool STREAM>
+__global__ void __launch_bounds__(kTailThreads) iteration_tail_kernel(DevProblem P, DevTail Z)
+{
+    if (*P.stop) return;
+    __shared__ double sp[kMaxDim + 1][kTailMaxVals];
+    __shared__ double sred[3][kTailThreads / 32];
+    __shared__ int s_flag;
+    const int n = P.n, np = P.np, ne = P.ne, dim = P.dim, nm = 1 + dim;
+    const int ch2 = np >> 1, epb = kTailThreads / ch2;
+    const int t = threadIdx.x, le = t / ch2, ch = t - le * ch2;
+    const int e = blockIdx.x * epb + le;
+    const bool valid = le < epb && e < ne;
+    const int i0 = 2 * ch;
+    const bool has1 = i0 + 1 < n;  // second dof of the chunk exists (n odd: the last chunk holds one dof and the zero padding)
+    const size_t block = (size_t)ne * n, x0 = (size_t)e * n + i0;
+    double v[kMaxDim + 1][2];
+#pragma unroll
+    for (int m = 0; m <= kMaxDim; ++m) v[m][0] = v[m][1] = 0.0;
+
+    if (STREAM)
+    {
+        // slot factors {mf, qf0, qf1, qf2} go through shared memory, 256 slots at a time
+        __shared__ double4 s_fac[kTailThreads];
+        const int s_begin = blockIdx.y * Z.slots_per_chunk, s_end = min(P.nslots, s_begin + Z.slots_per_chunk);
+        const size_t sblock = (size_t)ne * np;
+        const double *u = P.flux + (size_t)(valid ? e : 0) * np + i0;
+        auto add = [&](const double4 f, const double2 w) {
+            v[0][0] = fma(f.x, w.x, v[0][0]);
+            v[0][1] = fma(f.x, w.y, v[0][1]);
+            v[1][0] = fma(f.y, w.x, v[1][0]);
+            v[1][1] = fma(f.y, w.y, v[1][1]);
+            v[2][0] = fma(f.z, w.x, v[2][0]);
+            v[2][1] = fma(f.z, w.y, v[2][1]);
+            v[3][0] = fma(f.w, w.x, v[3][0]);
+            v[3][1] = fma(f.w, w.y, v[3][1]);
+        };
+        for (int sb = s_begin; sb < s_end; sb += kTailThreads)
+        {
+            const int se = min(s_end, sb + kTailThreads);
+            __syncthreads();
+            if (sb + t < se) s_fac[t] = make_double4(P.slot_mf[sb + t], P.slot_qf[3 * (sb + t)], P.slot_qf[3 * (sb + t) + 1], P.slot_qf[3 * (sb + t) + 2]);
+            __syncthreads();
+            if (!valid) continue;
+            int s = sb;
+            for (; s + 8 <= se; s += 8)
+            {
+                double2 w[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) w[k] = __ldcs(reinterpret_cast<const double2 *>(u + (size_t)(s + k) * sblock));
+#pragma unroll
+                for (int k = 0; k < 8; ++k) add(s_fac[s + k - sb], w[k]);
+            }
+            for (; s < se; ++s) add(s_fac[s - sb], __ldcs(reinterpret_cast<const double2 *>(u + (size_t)s * sblock)));
+        }
+        if (Z.nparts > 1)
+        {
+            if (valid)
+            {
+                double *pm = Z.part + (size_t)blockIdx.y * nm * block + x0;
+#pragma unroll
+                for (int m = 0; m <= kMaxDim; ++m)
+                {
+                    if (m >= nm) break;
+                    pm[(size_t)m * block] = v[m][0];
+                    if (has1) pm[(size_t)m * block + 1] = v[m][1];
+                }
+            }
+            if (!last_arrival(Z.tickets + blockIdx.x, (unsigned)Z.nparts, &s_flag)) return;
+        }
+    }
+    // ---- sum of the partial vectors, ascending (fixed order) ---------------------------------------------------------------
+    if (valid)
+    {
+        const int nparts = (STREAM && Z.nparts <= 1) ? -1 : Z.nparts;  // -1: v already holds the sums
+        if (nparts >= 0)
+        {
+#pragma unroll
+            for (int m = 0; m <= kMaxDim; ++m)
+            {
+                if (m >= nm) break;
+                double a = 0.0, b = 0.0;
+                if (nparts == 0)
+                {
+                    a = Z.mom[(size_t)m * block + x0];
+                    if (has1) b = Z.mom[(size_t)m * block + x0 + 1];
+                }
+                for (int y = 0; y < nparts; ++y)
+                {
+                    const double *pm = Z.part + ((size_t)y * nm + m) * block + x0;
+                    a += __ldcg(pm);
+                    if (has1) b += __ldcg(pm + 1);
+                }
+                v[m][0] = a;
+                v[m][1] = b;
+            }
+        }
+        if (nparts != 0)
+#pragma unroll
+            for (int m = 0; m <= kMaxDim; ++m)
+            {
+                if (m >= nm) break;
+                Z.mom[(size_t)m * block + x0] = v[m][0];
+                if (has1) Z.mom[(size_t)m * block + x0 + 1] = v[m][1];
+            }
+    }
+    if (!Z.finish) return;
+
+    // ---- finish: cell integrals, norms, hand-over ----------------------------------------------------------------------------
+    double c2 = 0.0;
+    if (valid)
+    {
+        const double b0 = Z.basis[x0], b1 = has1 ? Z.basis[x0 + 1] : 0.0;
+#pragma unroll
+        for (int m = 0; m <= kMaxDim; ++m)
+        {
+            if (m >= nm) break;
+            sp[m][le * n + i0] = v[m][0] * b0;
+            if (has1) sp[m][le * n + i0 + 1] = v[m][1] * b1;
+        }
+        // tc_prev rows are padded to np doubles; the padding stays zero
+        *reinterpret_cast<double2 *>(Z.tc_prev + (size_t)e * np + i0) = make_double2(v[0][0], has1 ? v[0][1] : 0.0);
+        c2 = v[0][0] * v[0][0] + (has1 ? v[0][1] * v[0][1] : 0.0);
+    }
+    __syncthreads();
+    double d2 = 0.0, t2 = 0.0;
+    {
+        // thread (m, element): sum over the dofs in ascending order, as the reference's loop does
+        const int nel = min(epb, ne - (int)blockIdx.x * epb);
+        for (int idx = t; idx < nm * nel; idx += kTailThreads)
+        {
+            const int m = idx / nel, l = idx - m * nel, ee = blockIdx.x * epb + l;
+            double s = 0.0;
+            for (int i = 0; i < n; ++i) s += sp[m][l * n + i];
+            Z.cell[(size_t)m * ne + ee] = s;
+            if (m == 0)
+            {
+                const double d = s - Z.tv_prev[ee];
+                d2 += d * d;
+                t2 += s * s;
+                Z.tv_prev[ee] = s;
+            }
+        }
+    }
+    // CTA partial sums in a fixed order: warp shuffle tree, then the warps in ascending order
+    for (int off = 16; off > 0; off >>= 1)
+    {
+        d2 += __shfl_down_sync(0xffffffffu, d2, off);
+        t2 += __shfl_down_sync(0xffffffffu, t2, off);
+        c2 += __shfl_down_sync(0xffffffffu, c2, off);
+    }
+    const int lane = t & 31, warp = t >> 5;
+    if (lane == 0)
+    {
+        sred[0][warp] = d2;
+        sred[1][warp] = t2;
+        sred[2][warp] = c2;
+    }
+    __syncthreads();
+    if (t < 3)
+    {
+        double a = 0.0;
+        for (int w = 0; w < kTailThreads / 32; ++w) a += sred[t][w];
+        Z.block_part[(size_t)blockIdx.x * 3 + t] = a;
+    }
+    if (!last_arrival(Z.tickets + gridDim.x, gridDim.x, &s_flag)) return;
+    // ---- last block of the grid: the three norms, history entry, stop test ----------------------------------------------------
+    double a[3] = {0.0, 0.0, 0.0};
+    for (int b = t; b < (int)gridDim.x; b += kTailThreads)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) a[k] += __ldcg(Z.block_part + (size_t)b * 3 + k);
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        for (int off = 16; off > 0; off >>= 1) a[k] += __shfl_down_sync(0xffffffffu, a[k], off);
+    __syncthreads();
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) sred[k][warp] = a[k];
+    __syncthreads();
+    if (t == 0)
+    {
+        double tot[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+        {
+            double s = 0.0;
+            for (int w = 0; w < kTailThreads / 32; ++w) s += sred[k][w];
+            tot[k] = s;
+        }
+        DevCtrl *c = Z.ctrl;
+        const int it = c->iter;
+        double *h = Z.hist + (size_t)(it % kHistRing) * 4;
+        h[0] = tot[0];
+        h[1] = tot[1];
+        h[2] = tot[2];
+        h[3] = (double)*P.error_flag;
+        c->iter = it + 1;
+        // the reference's stop test: res = ||Tv - Tv_prev|| / ||Tv|| < tol (src/PBTESolver.cpp:327)
+        if (tot[1] > 0.0 && sqrt(tot[0]) / sqrt(tot[1]) < c->tol) c->stop = 1;
+        __threadfence_system();
+    }
+}
+
+}  // namespace pbte_dev

@@ -72,8 +72,11 @@ CUDA_ABI_SYMBOLS = [
     "pbte_cuda_upload_moments", "pbte_cuda_download_moments", "pbte_cuda_sweep", "pbte_cuda_moment_buffer",
     "pbte_cuda_finish_iteration", "pbte_cuda_solve", "pbte_cuda_last_norms", "pbte_cuda_macro_reset",
     "pbte_cuda_macro_accumulate", "pbte_cuda_macro_finalize", "pbte_cuda_macro_residual", "pbte_cuda_get_stats",
-    "pbte_cuda_get_stream", "pbte_cuda_measure_peaks",
+    "pbte_cuda_get_stream", "pbte_cuda_measure_peaks", "pbte_cuda_iterate_async", "pbte_cuda_iterate_sync", "pbte_cuda_solve_ex",
+    "pbte_cuda_comm_get_unique_id", "pbte_cuda_comm_attach", "pbte_cuda_comm_attach_all", "pbte_cuda_comm_detach",
 ]
+COMM_ID_BYTES = 128
+ITER_CALLBACK = C.CFUNCTYPE(None, C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_double)
 
 _cuda = None
 _host = None
@@ -114,6 +117,14 @@ def cuda_lib():
         lib.pbte_cuda_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         lib.pbte_cuda_get_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         lib.pbte_cuda_measure_peaks.argtypes = [C.c_int, c_double_p, c_double_p, c_double_p]
+        lib.pbte_cuda_iterate_async.argtypes = [C.c_void_p]
+        lib.pbte_cuda_iterate_sync.argtypes = [C.c_void_p, C.POINTER(C.c_int64), c_double_p]
+        lib.pbte_cuda_solve_ex.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_double, c_int32_p, c_double_p, c_double_p,
+                                           ITER_CALLBACK, C.c_void_p]
+        lib.pbte_cuda_comm_get_unique_id.argtypes = [C.c_void_p]
+        lib.pbte_cuda_comm_attach.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
+        lib.pbte_cuda_comm_attach_all.argtypes = [C.POINTER(C.c_void_p), C.c_int32]
+        lib.pbte_cuda_comm_detach.argtypes = [C.c_void_p]
         lib.pbte_cuda_default_options.argtypes = [C.POINTER(Options)]
         lib.pbte_cuda_device_count.argtypes = [C.POINTER(C.c_int)]
         _cuda = lib
@@ -426,6 +437,24 @@ class Solver:
         _ck(self.lib.pbte_cuda_solve(self._h, max_iter, tol, C.byref(it), C.byref(r), _dp(hist)))
         return it.value, r.value, hist[: it.value]
 
+    def iterate_async(self):
+        """One whole source iteration enqueued (sweep, all-reduce when a communicator is attached, finish); no wait."""
+        _ck(self.lib.pbte_cuda_iterate_async(self._h))
+
+    def iterate_sync(self):
+        """Waits for everything enqueued; (iterations finished since the counters were reset, residual of the last one)."""
+        n, r = C.c_int64(0), C.c_double(0)
+        _ck(self.lib.pbte_cuda_iterate_sync(self._h, C.byref(n), C.byref(r)))
+        return n.value, r.value
+
+    def comm_attach(self, uid, rank, world_size):
+        """Collective over the ranks: NCCL communicator for the per-iteration all-reduce of [Tc | Qc]; uid = comm_unique_id() of rank 0."""
+        buf = (C.c_char * COMM_ID_BYTES).from_buffer_copy(bytes(uid))
+        _ck(self.lib.pbte_cuda_comm_attach(self._h, buf, rank, world_size))
+
+    def comm_detach(self):
+        _ck(self.lib.pbte_cuda_comm_detach(self._h))
+
     def stats(self):
         s = Stats()
         _ck(self.lib.pbte_cuda_get_stats(self._h, C.byref(s)))
@@ -452,6 +481,29 @@ class Solver:
         r = C.c_double(0)
         _ck(self.lib.pbte_cuda_macro_residual(self._h, _dp(prev_tv), C.byref(r)))
         return r.value
+
+
+def comm_unique_id():
+    """128 bytes that rank 0 creates and ships to the other ranks (pbte_cuda_comm_get_unique_id)."""
+    buf = (C.c_char * COMM_ID_BYTES)()
+    _ck(cuda_lib().pbte_cuda_comm_get_unique_id(buf))
+    return bytes(buf)
+
+
+def comm_attach_all(solvers):
+    """One process, several devices: a communicator set over the handles of `solvers` (one device each)."""
+    arr = (C.c_void_p * len(solvers))(*[s._h for s in solvers])
+    _ck(cuda_lib().pbte_cuda_comm_attach_all(arr, len(solvers)))
+
+
+def solve_multi(solvers, max_iter, tol=0.0, on_iteration=None):
+    """pbte_cuda_solve_ex over the handles of `solvers` (a single solver is allowed): (iterations, residual, history)."""
+    arr = (C.c_void_p * len(solvers))(*[s._h for s in solvers])
+    hist = np.zeros(max(max_iter, 1))
+    it, r = C.c_int32(0), C.c_double(0)
+    cb = ITER_CALLBACK(lambda user, i, res, tv, tc: on_iteration(i, res, tv, tc)) if on_iteration else ITER_CALLBACK()
+    _ck(cuda_lib().pbte_cuda_solve_ex(arr, len(solvers), max_iter, tol, C.byref(it), C.byref(r), _dp(hist), cb, None))
+    return it.value, r.value, hist[: it.value]
 
 
 def measure_peaks(device=-1):

@@ -150,12 +150,47 @@ int pbte_cuda_sweep(pbte_handle_t *h);
 /* Device pointer / length of the partial moment vector: multi-GPU callers all-reduce (sum) it in place
  * between pbte_cuda_sweep and pbte_cuda_finish_iteration (one collective per iteration). */
 int pbte_cuda_moment_buffer(pbte_handle_t *h, double **device_ptr, size_t *count);
-/* Finalize (Tv, Qv), residual ||Tv - Tv_prev|| / ||Tv||, then Tv_prev <- Tv, Tc_prev <- Tc. */
+/* Finalize (Tv, Qv), residual ||Tv - Tv_prev|| / ||Tv||, then Tv_prev <- Tv, Tc_prev <- Tc.  Waits for the result. */
 int pbte_cuda_finish_iteration(pbte_handle_t *h, double *residual);
 /* PBTESolver::Solve on one device: up to max_iter iterations, stops when residual < tol.
  * residual_history (may be NULL) receives one value per executed iteration. */
 int pbte_cuda_solve(pbte_handle_t *h, int32_t max_iter, double tol, int32_t *iters_done, double *residual,
                     double *residual_history);
+
+/* One whole source iteration ENQUEUED on the handle's stream and not waited for: sweep, the all-reduce of [Tc | Qc] when a
+ * communicator is attached, Finalize + Residual + hand-over (the body of the loop at src/PBTESolver.cpp:235-330).  On a
+ * single GPU this is two kernel launches (the marching sweep and a tail that streams the flux once and finishes the
+ * iteration), replayed as one CUDA graph.  pbte_cuda_iterate_sync waits for everything enqueued and returns the number of
+ * iterations finished since the last solve / reset of the counters and the residual of the last one. */
+int pbte_cuda_iterate_async(pbte_handle_t *h);
+int pbte_cuda_iterate_sync(pbte_handle_t *h, int64_t *iterations, double *last_residual);
+/* pbte_cuda_solve with a per-iteration callback (the line the reference prints, src/PBTESolver.cpp:318-326) and,
+ * for n_handles > 1, over several handles on several devices of ONE process (pbte_cuda_comm_attach_all first).
+ * The loop never synchronises between iterations: up to PBTE_LOOKAHEAD (default 4) iterations are in flight, the stop
+ * test res < tol is also evaluated on the device, and iterations enqueued beyond the stop are no-ops there, so the
+ * state left behind is that of the first iteration with res < tol, as in the reference. */
+typedef void (*pbte_iteration_callback_t)(void *user, int32_t iteration /*1-based*/, double residual, double tv_norm, double tc_fnorm);
+int pbte_cuda_solve_ex(pbte_handle_t *const *handles, int32_t n_handles, int32_t max_iter, double tol, int32_t *iters_done,
+                       double *residual, double *residual_history, pbte_iteration_callback_t on_iteration, void *user);
+
+/* ---- multi-GPU: the solver owns its communication ------------------------------------ */
+/* The (direction, band) space is partitioned by direction blocks (pbte_options_t::dir_begin/dir_end); the one exchange
+ * per iteration is an all-reduce (sum, FP64) of the per-DOF moment vector [Tc | Qc], issued by the library through NCCL
+ * on the handle's stream once a communicator is attached.  Replaces the gather + broadcast of Tc / residual of the
+ * reference's predecessor ("Reference Project/src/DGSolver/PBTE_NonGraySMRT_MPI.cpp":268-315) and the dead
+ * ExchangeFaceNbrData skeleton (src/PBTESolver.cpp:622-632).
+ *   one process per GPU:  rank 0 calls pbte_cuda_comm_get_unique_id and ships the 128 bytes to the other ranks (the
+ *                         launcher's own channel: MPI_Bcast, a file, torch.distributed ...); every rank then calls
+ *                         pbte_cuda_comm_attach(h, id, rank, world_size)   [collective]
+ *   one process, N GPUs:  pbte_cuda_comm_attach_all(handles, n) on n handles created on n different devices, then
+ *                         pbte_cuda_solve_ex(handles, n, ...)
+ * With a communicator attached pbte_cuda_finish_iteration / pbte_cuda_iterate_async / pbte_cuda_solve include the
+ * all-reduce, and pbte_cuda_moment_buffer is refused. */
+#define PBTE_COMM_ID_BYTES 128
+int pbte_cuda_comm_get_unique_id(void *id /*[PBTE_COMM_ID_BYTES]*/);
+int pbte_cuda_comm_attach(pbte_handle_t *h, const void *id, int32_t rank, int32_t world_size);
+int pbte_cuda_comm_attach_all(pbte_handle_t *const *handles, int32_t n_handles);
+int pbte_cuda_comm_detach(pbte_handle_t *h);
 
 /* ||Tv||_2 and ||Tc||_F of the last finish_iteration (the two norms the reference prints per iteration,
  * src/PBTESolver.cpp:318-326). */

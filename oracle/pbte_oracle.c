@@ -5,7 +5,7 @@
  * (include/pbte_cuda.h) that the CUDA library consumes.  Only tests/, __graft_entry__.smoke() and the
  * cpu_baseline / --impl reference legs of bench.py may load this file's library; the product never does.
  *
- * Parity status: PINNED.  This restatement is checked (tests/test_oracle_vs_reference.py) against
+ * Parity status: PINNED.  This restatement is checked (tests/test_oracle_golden.py) against
  *   (1) the reference's own sources compiled unmodified against the mfem_lite stand-in (oracle/_ref), which
  *       reproduce every golden log the reference ships (output/log/*, the decoded VTU, T_slice.txt), and
  *   (2) the committed golden fixtures generated from that build (tests/golden/).
