@@ -190,40 +190,74 @@ void Vector::GetSubVector(const Array<int> &dofs, Vector &ev) const
 }
 
 // ------------------------------------------------------------------ DenseMatrix
-DenseMatrix::DenseMatrix(DenseMatrix &&o) noexcept : d_(std::move(o.d_)), h_(o.h_), w_(o.w_) { o.h_ = o.w_ = 0; }
+DenseMatrix::DenseMatrix(const DenseMatrix &o) : d_(o.Data(), o.Data() + o.Count()), h_(o.h_), w_(o.w_) {}
+
+DenseMatrix::DenseMatrix(DenseMatrix &&o) noexcept : d_(std::move(o.d_)), ext_(o.ext_), h_(o.h_), w_(o.w_)
+{
+    o.ext_ = nullptr;
+    o.h_ = o.w_ = 0;
+}
+
+DenseMatrix &DenseMatrix::operator=(const DenseMatrix &o)
+{
+    if (this == &o) return *this;
+    if (h_ != o.h_ || w_ != o.w_)
+    {
+        ext_ = nullptr;
+        h_ = o.h_;
+        w_ = o.w_;
+        d_.assign(o.Data(), o.Data() + o.Count());
+    }
+    else if (Count()) std::memcpy(Data(), o.Data(), sizeof(double) * Count());
+    return *this;
+}
 
 DenseMatrix &DenseMatrix::operator=(DenseMatrix &&o) noexcept
 {
     d_ = std::move(o.d_);
+    ext_ = o.ext_;
     h_ = o.h_;
     w_ = o.w_;
+    o.ext_ = nullptr;
     o.h_ = o.w_ = 0;
     return *this;
 }
 
 DenseMatrix &DenseMatrix::operator=(double v)
 {
-    std::fill(d_.begin(), d_.end(), v);
+    std::fill(Data(), Data() + Count(), v);
     return *this;
 }
 
 void DenseMatrix::SetSize(int h, int w)
 {
     if (h == h_ && w == w_) return;
+    ext_ = nullptr;
     h_ = h;
     w_ = w;
     d_.assign(static_cast<size_t>(h) * w, 0.0);
 }
 
+void DenseMatrix::UseExternalData(double *d, int h, int w)
+{
+    std::vector<double>().swap(d_);
+    ext_ = d;
+    h_ = h;
+    w_ = w;
+}
+
 DenseMatrix &DenseMatrix::operator*=(double c)
 {
-    for (double &x : d_) x *= c;
+    double *p = Data();
+    for (size_t i = 0, n = Count(); i < n; ++i) p[i] *= c;
     return *this;
 }
 
 DenseMatrix &DenseMatrix::operator+=(const DenseMatrix &A)
 {
-    for (size_t i = 0; i < d_.size(); ++i) d_[i] += A.d_[i];
+    double *p = Data();
+    const double *q = A.Data();
+    for (size_t i = 0, n = Count(); i < n; ++i) p[i] += q[i];
     return *this;
 }
 
@@ -240,7 +274,7 @@ void DenseMatrix::Mult(const double *x, double *y) const
         for (int r = 0; r < h_; ++r) y[r] = 0.0;
         return;
     }
-    const double *col = d_.data();
+    const double *col = Data();
     double xc = x[0];
     for (int r = 0; r < h_; ++r) y[r] = xc * col[r];
     col += h_;
@@ -256,7 +290,7 @@ void DenseMatrix::Mult(const Vector &x, Vector &y) const { Mult(x.GetData(), y.G
 
 void DenseMatrix::MultTranspose(const Vector &x, Vector &y) const
 {
-    const double *col = d_.data();
+    const double *col = Data();
     for (int c = 0; c < w_; ++c)
     {
         double s = 0.0;
@@ -269,12 +303,12 @@ void DenseMatrix::MultTranspose(const Vector &x, Vector &y) const
 void DenseMatrix::GetColumn(int c, Vector &col) const
 {
     col.SetSize(h_);
-    std::memcpy(col.GetData(), d_.data() + static_cast<size_t>(c) * h_, sizeof(double) * h_);
+    std::memcpy(col.GetData(), Data() + static_cast<size_t>(c) * h_, sizeof(double) * h_);
 }
 
 void DenseMatrix::SetCol(int c, const Vector &col)
 {
-    std::memcpy(d_.data() + static_cast<size_t>(c) * h_, col.GetData(), sizeof(double) * h_);
+    std::memcpy(Data() + static_cast<size_t>(c) * h_, col.GetData(), sizeof(double) * h_);
 }
 
 void DenseMatrix::Transpose()
@@ -294,6 +328,7 @@ void DenseMatrix::Transpose()
 void DenseMatrix::Swap(DenseMatrix &o)
 {
     d_.swap(o.d_);
+    std::swap(ext_, o.ext_);
     std::swap(h_, o.h_);
     std::swap(w_, o.w_);
 }
@@ -301,12 +336,14 @@ void DenseMatrix::Swap(DenseMatrix &o)
 double DenseMatrix::FNorm() const
 {
     double mx = 0.0;
-    for (double x : d_) mx = std::max(mx, std::fabs(x));
+    const double *p = Data();
+    const size_t cnt = Count();
+    for (size_t i = 0; i < cnt; ++i) mx = std::max(mx, std::fabs(p[i]));
     if (mx == 0.0) return 0.0;
     double s = 0.0;
-    for (double x : d_)
+    for (size_t i = 0; i < cnt; ++i)
     {
-        const double e = x / mx;
+        const double e = p[i] / mx;
         s += e * e;
     }
     return mx * std::sqrt(s);
@@ -314,7 +351,7 @@ double DenseMatrix::FNorm() const
 
 double DenseMatrix::Det() const
 {
-    const double *d = d_.data();
+    const double *d = Data();
     switch (h_)
     {
         case 0: return 1.0;
@@ -338,7 +375,7 @@ double DenseMatrix::Det() const
 double DenseMatrix::Weight() const
 {
     if (h_ == w_) return Det();
-    const double *d = d_.data();
+    const double *d = Data();
     if (h_ == 2 && w_ == 1) return std::sqrt(d[0] * d[0] + d[1] * d[1]);
     if (h_ == 3 && w_ == 1) return std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
     if (h_ == 3 && w_ == 2)

@@ -169,25 +169,29 @@ public:
     DenseMatrix() = default;
     explicit DenseMatrix(int s) { SetSize(s, s); }
     DenseMatrix(int h, int w) { SetSize(h, w); }
-    DenseMatrix(const DenseMatrix &o) = default;
+    /// View of caller-owned storage (never freed here), as in MFEM.
+    DenseMatrix(double *d, int h, int w) { UseExternalData(d, h, w); }
+    DenseMatrix(const DenseMatrix &o);  // deep copy into owned storage
     DenseMatrix(DenseMatrix &&o) noexcept;
-    DenseMatrix &operator=(const DenseMatrix &o) = default;
+    DenseMatrix &operator=(const DenseMatrix &o);
     DenseMatrix &operator=(DenseMatrix &&o) noexcept;
     DenseMatrix &operator=(double v);
 
     void SetSize(int s) { SetSize(s, s); }
     void SetSize(int h, int w);
+    void UseExternalData(double *d, int h, int w);
+    bool OwnsData() const { return ext_ == nullptr; }
     int Height() const { return h_; }
     int Width() const { return w_; }
     int NumRows() const { return h_; }
     int NumCols() const { return w_; }
-    double *Data() { return d_.data(); }
-    const double *Data() const { return d_.data(); }
-    double *GetData() { return d_.data(); }
-    const double *GetData() const { return d_.data(); }
+    double *Data() { return ext_ ? ext_ : d_.data(); }
+    const double *Data() const { return ext_ ? ext_ : d_.data(); }
+    double *GetData() { return Data(); }
+    const double *GetData() const { return Data(); }
 
-    double &operator()(int i, int j) { return d_[i + static_cast<size_t>(j) * h_]; }
-    const double &operator()(int i, int j) const { return d_[i + static_cast<size_t>(j) * h_]; }
+    double &operator()(int i, int j) { return Data()[i + static_cast<size_t>(j) * h_]; }
+    const double &operator()(int i, int j) const { return Data()[i + static_cast<size_t>(j) * h_]; }
 
     DenseMatrix &operator*=(double c);
     DenseMatrix &operator+=(const DenseMatrix &A);
@@ -207,7 +211,9 @@ public:
     double Weight() const;
 
 private:
+    size_t Count() const { return static_cast<size_t>(h_) * w_; }
     std::vector<double> d_;
+    double *ext_ = nullptr;  // non-null: view of external storage
     int h_ = 0, w_ = 0;
 };
 

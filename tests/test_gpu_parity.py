@@ -1,11 +1,12 @@
 """GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the same inputs and
 against the committed golden fixtures generated from the reference's own code.
 
-Bars: sweep schedules bit-exact; Tc / Qc / flux within 1e-10 relative (FP64) per iteration for the cases whose local
-systems are well conditioned.  Three cases are run with the reference's default face rule on
-high-order quads/hexes, where the source iteration itself is unstable (residuals grow, local systems are nearly
-singular); there every FP64 implementation that does not replay the reference's exact operation order differs at
-cond(A)*eps, the tolerance is stated per case, and the same cases are ALSO run with consistent face traces at 1e-10.
+Bars: sweep schedules bit-exact; Tc / Qc / flux within 1e-10 relative (FP64).  Two cases (quad order 4, hex order 3) are run
+with the reference's default face rule, under which their local systems have cond(A) up to 5e7: every FP64
+implementation that does not replay the reference's exact operation order differs by about cond(A) * eps there, the per-element
+LU kernels (MFEM's pivoting) included.  Their bound is computed from the measured cond(A) (tests/parity_tol.py: 2.6e-9 and
+8e-10 against measured errors of 1e-10 .. 5e-10, profiles/r02_tolerance_probe.txt); the same cases ALSO run with consistent face
+traces at 1e-10.
 """
 import numpy as np
 import pytest
@@ -14,11 +15,23 @@ import oracle as orc
 import pbte_b200 as pb
 from cases import CASES, host_case
 from conftest import golden
+from parity_tol import parity_tolerance
 
 pytestmark = pytest.mark.gpu
 
-TOL = {name: 1e-10 for name in CASES}
-TOL.update(quad_p4=1e-5, hex_p3=1e-8)  # ill-conditioned under quirk Q1, see module docstring
+ILL_CONDITIONED = ("quad_p4", "hex_p3")  # under quirk Q1, see module docstring
+_tol_cache = {}
+
+
+def tol_of(name, P):
+    """1e-10, or the conditioning bound of tests/parity_tol.py for the two ill-conditioned Q1 cases."""
+    if name not in ILL_CONDITIONED:
+        return 1e-10
+    if name not in _tol_cache:
+        _tol_cache[name] = parity_tolerance(P, name)
+    return _tol_cache[name]
+
+
 ALL = ["c0_default", "c1_tri_p1", "tri_p3_si", "quad_p2", "quad_p4", "tet_p1", "tet_p2", "hex_p1", "c2_hex_p2_small", "hex_p3", "quad_p1_dim3"]
 
 
@@ -51,7 +64,7 @@ def test_cuda_matches_oracle(name, kernel, policy):
     want = orc.solve(P, iters, 0.0, cache_lu=True, threads=8)
     got = gpu_solve(P, iters, kernel=kernel, cache_policy=policy)
     assert np.array_equal(got["orders"], orc.sweep_orders(P))  # bit-exact schedules
-    tol = TOL[name]
+    tol = tol_of(name, P)
     for k in ("Tc", "Qc", "Tv", "Qv", "coeff"):
         assert rel(got[k], want[k]) <= tol, (k, rel(got[k], want[k]))
     assert np.allclose(got["residuals"], want["residuals"], rtol=max(tol * 10, 1e-9), atol=0)
@@ -116,7 +129,7 @@ def test_marching_variants_on_single_class_meshes(name, variant, monkeypatch):
     assert got["stats"].kernel_used == 3 and got["stats"].march_variant == variant
     assert np.array_equal(got["orders"], orc.sweep_orders(P))
     for k in ("Tc", "Qc", "Tv", "Qv", "coeff"):
-        assert rel(got[k], want[k]) <= TOL[name], (k, rel(got[k], want[k]))
+        assert rel(got[k], want[k]) <= tol_of(name, P), (k, rel(got[k], want[k]))
     hc.close()
 
 
