@@ -1,15 +1,18 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the PBTE sweep: DOF*angle*band updates per second per source iteration.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--no-strong]
 
 Workload (BASELINE.json configs[1], SURVEY §8d "C2"): builtin unit-cube-hex 4x4x4 refined twice (4096 hexes), DG order 2
 (ndof 27), 8 Gauss polar x 16 uniform azimuth directions (128), "gray" = num_spectral 1 (2 bands), walls -0.5 / top +0.5,
-local matrices as the reference assembles them.  One step = one source iteration: upwind sweeps of every (direction, band)
-over the mesh, fused moments, [all-reduce of the moment vector for N > 1], cell integrals + residual.
+local matrices as the reference assembles them.  One step = one source iteration (pbte_cuda_iterate_async): upwind sweeps of
+every (direction, band) over the mesh, one tail kernel that streams the flux for the moments and finishes the iteration (cell
+integrals, residual, stop test) [for N > 1: moments, the library's NCCL all-reduce of the moment vector, finish].  The K timed
+steps are enqueued back to back without host synchronisation, as pbte_cuda_solve runs them.
 N > 1 (torchrun, one process per GPU): every rank sweeps its own block of directions over the whole mesh; the azimuth count
-grows with N (16*N), so per-GPU work is fixed ("weak" scaling) and the one NCCL all-reduce per iteration is the only
-data-path collective.
+grows with N (16*N), so per-GPU work is fixed ("weak" scaling) and the one NCCL all-reduce per iteration, issued by the
+library on its own communicator (pbte_cuda_comm_attach), is the only data-path collective.  Every N also carries a
+`strong_scaling` record: BASELINE's non-gray 3-D Si case C3 at full size, its 128 directions split over the N GPUs.
 
 Timed with CUDA events on the sweep stream, barrier + synchronize on both sides, max over ranks.  The flux (226 MB per
 128 directions) and the matrix image (0.4 GB) together exceed the 126 MB L2 every step, so no explicit flush is needed.
@@ -33,7 +36,15 @@ METRIC = "DOF*angle*band updates/s per sweep"
 UNIT = "updates/s"
 BC3 = {1: -0.5, 2: -0.5, 3: -0.5, 4: -0.5, 5: -0.5, 6: 0.5}
 WORKLOAD = dict(mesh="unit-cube-hex", order=2, refine=2, angle_dim=3, polar=8, azimuth=16, num_spectral=1)
-SAMPLE = dict(WORKLOAD, refine=1)  # CPU legs: same workload one refinement level down (512 hexes), updates/s is size independent
+WORKLOAD_NAME = "C2: builtin unit-cube-hex refine 2 (4096 hexes), DG order 2 (ndof 27), 8 Gauss polar x 16 uniform azimuth directions per GPU, gray SMRT = 2 bands"
+# CPU legs: the SAME mesh, order, bands and polar rule; a step sweeps a bounded number of azimuth points (the cost of a direction
+# does not depend on how many others there are), chosen so that the run ends within minutes and the reference's LU cache stays small
+CPU_MAX_AZIMUTH = 4
+
+
+def cpu_sample_azimuth(steps, warmup, budget_s=150.0, s_per_direction=0.04):
+    """Azimuth points of the CPU sample: (steps + warmup) x 8 polar x azimuth x ~40 ms per direction within the budget."""
+    return int(max(1, min(CPU_MAX_AZIMUTH, budget_s / (max(steps + warmup, 1) * 8 * s_per_direction))))
 # --workload: the other BASELINE configs at their real sizes (extra measurements, profiles/README.md; the default stays C2, the
 # configuration the metric is quoted on).  C2 is weak-scaled (128 directions per GPU); these keep the named quadrature and split
 # its directions over the GPUs (strong scaling)
@@ -164,95 +175,209 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU implementation (its unmodified sources against the MFEM stand-in,
-    oracle/_ref), serial as the reference is; falls back to the C port when oracle/_ref is absent."""
-    if rank != 0:
-        return
+def cpu_reference_run(steps, warmup, azimuth, threads_for_port=None):
+    """The reference's own CPU implementation (its unmodified sources against the MFEM stand-in, oracle/_ref; serial, as the
+    reference is) on the benchmark's mesh / order / bands with `azimuth` azimuth points; the C port when oracle/_ref is absent."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as orc
     import pbte_b200 as pb
+    wl = WORKLOAD
     mat = dict(pb.SI_MATERIAL)
-    mat["num_spectral"] = SAMPLE["num_spectral"]
-    azim = SAMPLE["azimuth"]  # the sample keeps 128 directions whatever N is
+    mat["num_spectral"] = wl["num_spectral"]
     times = []
     if orc.ref_available():
         kind, cores = "reference", 1
-        rc = orc.RefCase(SAMPLE["mesh"], SAMPLE["order"], SAMPLE["refine"], SAMPLE["angle_dim"], SAMPLE["polar"], azim, True, False, BC3, mat)
+        rc = orc.RefCase(wl["mesh"], wl["order"], wl["refine"], wl["angle_dim"], wl["polar"], azimuth, True, False, BC3, mat)
         U = rc.ndof * rc.ne * rc.ndir * rc.nband
         rs = orc.RefSolver(rc, 1, 0)
         ctor = rs.ctor_seconds
-        for i in range(args.warmup + args.steps):
+        for i in range(warmup + steps):
             _, secs = rs.solve()
-            if i >= args.warmup:
+            if i >= warmup:
                 times.append(secs)
-        sizes = rc.sizes
+        ne, ndir, nband = rc.ne, rc.ndir, rc.nband
+        rs.close()
+        rc.close()
     else:
-        kind, cores = "port", os.cpu_count() or 1
-        hc = pb.HostCase(SAMPLE["mesh"], SAMPLE["order"], SAMPLE["refine"], SAMPLE["angle_dim"], SAMPLE["polar"], azim, True, False, BC3,
-                         num_spectral=SAMPLE["num_spectral"])
+        kind, cores = "port", threads_for_port or (os.cpu_count() or 1)
+        hc = pb.HostCase(wl["mesh"], wl["order"], wl["refine"], wl["angle_dim"], wl["polar"], azimuth, True, False, BC3, num_spectral=wl["num_spectral"])
         P = hc.problem
         U = P.updates_per_sweep
         ctor = 0.0
         state = None
-        for i in range(args.warmup + args.steps):
+        for i in range(warmup + steps):
             t0 = time.perf_counter()
             r = orc.solve(P, 1, 0.0, cache_lu=False, threads=cores, **(state or {}))
             secs = time.perf_counter() - t0
             state = dict(coeff=r["coeff"], Tc=r["Tc"], Tv=r["Tv"])
-            if i >= args.warmup:
+            if i >= warmup:
                 times.append(secs)
-        sizes = P
+        ne, ndir, nband = P.ne, P.ndir, P.nband
+        hc.close()
     t = float(np.mean(times))
-    value = U / t
-    sample = (f"{SAMPLE['mesh']} refine {SAMPLE['refine']} ({sizes.ne} hexes), order 2, {sizes.ndir} directions, {sizes.nband} bands: "
-              f"{U} updates per step; PBTESolver::Solve only (constructor with its LU cache took {ctor:.1f} s, not timed)")
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    sample = (f"{'reference sources (-O2, serial as the reference is; its MPI path is dead code: n/a)' if kind == 'reference' else 'C restatement, all host cores'}"
+              f" on the benchmark's own mesh ({wl['mesh']} refine {wl['refine']}: {ne} hexes), order 2, 2 bands, 8 polar x {azimuth} azimuth = {ndir} of the 128"
+              f" directions per step ({U} updates; a direction's sweep costs the same whatever the number of directions); {steps} timed PBTESolver::Solve"
+              f" iterations after {warmup} warm-up; constructor with its FullLU cache {ctor:.1f} s, not timed")
+    return {"value": U / t, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}, t
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference arm of the driver.  Rank 0 alone runs it."""
+    if rank != 0:
+        return
+    base, t = cpu_reference_run(args.steps, args.warmup, cpu_sample_azimuth(args.steps, args.warmup))
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C2: unit-cube-hex refine 2 (4096 hexes), order 2, 8x16 directions, 2 bands (gray SMRT); CPU arm runs the bounded sample below"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+            "config": {"workload": WORKLOAD_NAME, "parallelism": "host cores of the GPU box", "sample": base["sample"]},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-# ---------------------------------------------------------------------------------------------------------------
-def cpu_baseline_leg(budget_s=25.0):
-    """Rank 0, N = 1: the reference CPU path on a bounded sample, timed beside the GPU numbers."""
+def cpu_baseline_leg():
+    """Rank 0, N = 1: the reference CPU path on a bounded sample of the same workload, timed beside the GPU numbers, and — as a
+    labelled extra — the C port threaded over (direction, band) on all host cores."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as orc
     import pbte_b200 as pb
-    mat = dict(pb.SI_MATERIAL)
-    mat["num_spectral"] = SAMPLE["num_spectral"]
-    out = {}
-    if orc.ref_available():
-        rc = orc.RefCase(SAMPLE["mesh"], SAMPLE["order"], SAMPLE["refine"], SAMPLE["angle_dim"], SAMPLE["polar"], SAMPLE["azimuth"], True, False, BC3, mat)
-        U = rc.ndof * rc.ne * rc.ndir * rc.nband
-        rs = orc.RefSolver(rc, 1, 0)
-        times = []
-        t_start = time.perf_counter()
-        while len(times) < 4 and time.perf_counter() - t_start < budget_s:
-            times.append(rs.solve()[1])
-        t = float(np.mean(times[1:] if len(times) > 1 else times))
-        out = {"value": U / t, "unit": UNIT, "cores": 1, "kind": "reference",
-               "sample": f"reference sources (-O2) on {SAMPLE['mesh']} refine {SAMPLE['refine']} ({rc.ne} hexes), order 2, {rc.ndir} directions, {rc.nband} bands; "
-                         f"{len(times)} Solve iterations of {U} updates, FullLU cache built once in {rs.ctor_seconds:.1f} s (not timed); MPI path: n/a (dead code in the reference)"}
-        rs.close()
-        rc.close()
-    # labelled extra: the C port threaded over (direction, band) on all host cores
-    hc = pb.HostCase(SAMPLE["mesh"], SAMPLE["order"], SAMPLE["refine"], SAMPLE["angle_dim"], SAMPLE["polar"], SAMPLE["azimuth"], True, False, BC3,
-                     num_spectral=SAMPLE["num_spectral"])
-    cores = os.cpu_count() or 1
-    t0 = time.perf_counter()
-    orc.solve(hc.problem, 2, 0.0, cache_lu=False, threads=cores)
-    tp = (time.perf_counter() - t0) / 2
-    port = {"value": hc.problem.updates_per_sweep / tp, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "C restatement, LU on the fly, (direction,band) sweeps on all host cores, same sample mesh, 2 iterations"}
-    hc.close()
-    if not out:
-        out = port
-    else:
-        out["threaded_port"] = port
+    out, _ = cpu_reference_run(3, 1, 2)
+    if out["kind"] == "reference":
+        wl = WORKLOAD
+        hc = pb.HostCase(wl["mesh"], wl["order"], wl["refine"], wl["angle_dim"], wl["polar"], 4, True, False, BC3, num_spectral=wl["num_spectral"])
+        cores = os.cpu_count() or 1
+        orc.solve(hc.problem, 1, 0.0, cache_lu=False, threads=cores)
+        t0 = time.perf_counter()
+        orc.solve(hc.problem, 2, 0.0, cache_lu=False, threads=cores)
+        tp = (time.perf_counter() - t0) / 2
+        out["threaded_port"] = {"value": hc.problem.updates_per_sweep / tp, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "C restatement, LU on the fly, (direction, band) sweeps on all host cores, same mesh, 8 x 4 directions, 2 iterations"}
+        hc.close()
     return out
+
+
+class Plumbing:
+    """torch.distributed for what is not the data path: barrier, max over ranks, shipping the communicator id."""
+
+    def __init__(self, rank, world, local_rank):
+        import torch
+        self.torch, self.rank, self.world, self.local_rank = torch, rank, world, local_rank
+        self.dist = None
+        self.saved_stdout = None
+        if world > 1:
+            # NCCL may print a banner on stdout when a communicator is created (NCCL_DEBUG=VERSION/INFO from the environment, which is
+            # respected): stdout is kept for the one JSON line by pointing fd 1 at stderr until the warm-up is over
+            sys.stdout.flush()
+            self.saved_stdout = os.dup(1)
+            os.dup2(2, 1)
+            import torch.distributed as dist
+            self.dist = dist
+            dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+
+    def restore_stdout(self):
+        if self.saved_stdout is not None:
+            sys.stdout.flush()
+            os.dup2(self.saved_stdout, 1)
+            os.close(self.saved_stdout)
+            self.saved_stdout = None
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=f"cuda:{self.local_rank}")
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def attach(self, solver, pb):
+        """The library's own NCCL communicator for the per-iteration all-reduce: rank 0's id goes to the others through torch."""
+        if self.dist is None:
+            return
+        buf = self.torch.zeros(pb.COMM_ID_BYTES, dtype=self.torch.uint8, device=f"cuda:{self.local_rank}")
+        if self.rank == 0:
+            buf.copy_(self.torch.frombuffer(bytearray(pb.comm_unique_id()), dtype=self.torch.uint8))
+        self.dist.broadcast(buf, src=0)
+        solver.comm_attach(bytes(buf.cpu().numpy().tobytes()), self.rank, self.world)
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+def timed_iterations(solver, plumb, stream, steps, warmup, sampler=None):
+    """W warm-up iterations, then EXACTLY `steps` iterations enqueued back to back (no host synchronisation between them),
+    CUDA events on the sweep stream, barrier + synchronize on both sides; returns (ms of the timed region: max over ranks,
+    residual of the last iteration, clocks, launches inside the timed region)."""
+    torch = plumb.torch
+    with torch.cuda.stream(stream):
+        for _ in range(warmup):
+            solver.iterate_async()
+        solver.iterate_sync()
+        plumb.barrier()
+        plumb.restore_stdout()
+        if sampler is not None:
+            sampler.start()
+        st0 = solver.stats()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(steps):
+            solver.iterate_async()
+        ev1.record(stream)
+        _, res = solver.iterate_sync()
+        plumb.barrier()
+        clocks = sampler.stop() if sampler is not None else None
+        st1 = solver.stats()
+    return plumb.max(ev0.elapsed_time(ev1)), res, clocks, int(st1.kernel_launches - st0.kernel_launches)
+
+
+def sampled_kernel_times(solver, stream, torch, n=10):
+    """Duration of the sweep and of its dominant kernel, sampled over `n` more iterations of the same state with one
+    synchronisation per iteration (the library's own CUDA events: before the sweep, behind the marching kernel, behind the tail)."""
+    sweep_ms, march_ms = [], []
+    with torch.cuda.stream(stream):
+        for _ in range(n):
+            solver.iterate_async()
+            solver.iterate_sync()
+            st = solver.stats()
+            sweep_ms.append(st.last_sweep_ms)
+            march_ms.append(st.last_march_ms)
+    return float(np.mean(sweep_ms)), float(np.mean(march_ms))
+
+
+def strong_scaling_leg(args, plumb, pb, stream):
+    """BASELINE's non-gray 3-D Si case (C3: 196 608 tetrahedra order 2, 8 x 16 directions, 40 bands, 1.007e10 updates per
+    iteration, 80.5 GB of flux) at its full size, the 128 directions split over the N GPUs: total work fixed = strong scaling."""
+    torch, rank, world, local_rank = plumb.torch, plumb.rank, plumb.world, plumb.local_rank
+    wl = EXTRA_WORKLOADS["c3"]
+    t_setup = time.perf_counter()
+    hc = pb.HostCase(wl["mesh"], wl["order"], wl["refine"], wl["angle_dim"], wl["polar"], wl["azimuth"], True, False, BC3, num_spectral=wl["num_spectral"])
+    P = hc.problem
+    k0, k1 = pb.partition_directions(P.ndir, world, rank)
+    solver = pb.Solver(P, device=local_rank, dir_range=(k0, k1), cache_policy=0, kernel=0, stream=stream.cuda_stream)
+    nclass, nlev = solver.build_schedule()
+    plumb.attach(solver, pb)
+    setup_s = time.perf_counter() - t_setup
+    steps = 5
+    total_ms, res, _, launches = timed_iterations(solver, plumb, stream, steps, 2)
+    sweep_ms, march_ms = sampled_kernel_times(solver, stream, torch, 2)
+    st = solver.stats()
+    U = P.updates_per_sweep
+    U_rank = P.ndof * P.ne * (k1 - k0) * P.nband
+    peaks, peak_src = load_measured_peaks()
+    kern_s = (march_ms if march_ms > 0 else sweep_ms) * 1e-3
+    rec = {"workload": wl["label"], "scaling": "strong", "n_gpus": world, "value": U * steps / (total_ms * 1e-3), "unit": UNIT, "steps": steps,
+           "ms_per_step": total_ms / steps, "updates_per_step": U, "directions_per_gpu": k1 - k0, "slots_per_gpu": (k1 - k0) * P.nband,
+           "kernel_used": st.kernel_used, "operator_classes": st.n_operator_classes, "upwind_dags": nclass, "wavefront_levels": nlev, "tile_fill": st.march_fill,
+           "flux_gb_per_gpu": st.flux_bytes / 1e9, "setup_seconds": setup_s, "residual": res, "gpu_launches": launches,
+           "roofline": {"bound": "hbm", "achieved": 16.0 * U_rank / kern_s / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                        "frac": 16.0 * U_rank / kern_s / 1e9 / peaks.get("hbm_gbs"), "kernel_ms": kern_s * 1e3, "peak_source": peak_src,
+                        "note": "16 B/update (flux read once, written once) over the marching kernel's duration on rank 0"}}
+    solver.close()
+    hc.close()
+    return rec
 
 
 def run_gpu(args, rank, world, local_rank):
@@ -261,119 +386,52 @@ def run_gpu(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
-    dist = None
-    saved_stdout = None
-    if world > 1:
-        # NCCL prints its version banner on stdout when a communicator is created: keep stdout for the one JSON line by pointing
-        # fd 1 at stderr until the warm-up is over
-        sys.stdout.flush()
-        saved_stdout = os.dup(1)
-        os.dup2(2, 1)
-        import torch.distributed as dist_mod
-        dist = dist_mod
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keeps NCCL's version banner off stdout: rank 0 prints exactly one JSON line
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+    plumb = Plumbing(rank, world, local_rank)
 
     wl = EXTRA_WORKLOADS.get(args.workload, WORKLOAD)
     strong = args.workload in EXTRA_WORKLOADS
     azim = wl["azimuth"] * (1 if strong else world)
+    t_setup = time.perf_counter()
     hc = pb.HostCase(wl["mesh"], wl["order"], wl["refine"], wl["angle_dim"], wl["polar"], azim, True, False, wl.get("bcs", BC3), num_spectral=wl["num_spectral"])
+    host_setup_s = time.perf_counter() - t_setup
     P = hc.problem
     k0, k1 = pb.partition_directions(P.ndir, world, rank)
     stream = torch.cuda.Stream(device=local_rank)
+    t_setup = time.perf_counter()
     solver = pb.Solver(P, device=local_rank, dir_range=(k0, k1), cache_policy=0, kernel=args.kernel, stream=stream.cuda_stream)
     nclass, nlev = solver.build_schedule()
-    ptr, count = solver.moment_buffer()
-    # the moment vector as a torch tensor over the library's device buffer: what NCCL all-reduces in place
-    mom = None
-    if world > 1:
-        class _Buf:
-            __cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 3, "strides": None}
-        mom = torch.as_tensor(_Buf(), device=torch.device("cuda", local_rank))
+    device_setup_s = time.perf_counter() - t_setup
+    plumb.attach(solver, pb)
 
-    phase_ev = []  # BENCH_PHASES=1: CUDA events around the all-reduce of every step (diagnostics on stderr)
-
-    def step():
-        solver.sweep()
-        if mom is not None:
-            if os.environ.get("BENCH_PHASES"):
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(stream)
-                dist.all_reduce(mom, op=dist.ReduceOp.SUM)
-                e1.record(stream)
-                phase_ev.append((e0, e1))
-            else:
-                dist.all_reduce(mom, op=dist.ReduceOp.SUM)
-        return solver.finish_iteration()
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler is not None:
         sampler.launch()
-    with torch.cuda.stream(stream):
-        for _ in range(max(args.warmup, 3)):
-            step()
-        barrier()
-        if saved_stdout is not None:
-            sys.stdout.flush()
-            os.dup2(saved_stdout, 1)
-            os.close(saved_stdout)
-        if rank == 0:
-            sampler.start()
-        st0 = solver.stats()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sweep_ms, march_ms = [], []
-        ev0.record(stream)
-        for _ in range(args.steps):
-            res = step()
-            stx = solver.stats()
-            sweep_ms.append(stx.last_sweep_ms)
-            march_ms.append(stx.last_march_ms)
-        ev1.record(stream)
-        barrier()
-        clocks = sampler.stop() if rank == 0 else None
-        st1 = solver.stats()
-    total_ms = ev0.elapsed_time(ev1)
-    if phase_ev:
-        ar = [a.elapsed_time(b) for a, b in phase_ev[-args.steps:]]
-        print(f"[rank {rank}] phases per step: sweep {np.mean(sweep_ms):.3f} ms, all-reduce (device, incl. waiting for the peers) {np.mean(ar):.3f} ms "
-              f"(min {min(ar):.3f}), finish {solver.stats().last_finish_ms:.3f} ms, step {total_ms / args.steps:.3f} ms", file=sys.stderr, flush=True)
-    t = torch.tensor([total_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
+    total_ms, res, clocks, launches = timed_iterations(solver, plumb, stream, args.steps, max(args.warmup, 3), sampler)
     U = P.updates_per_sweep  # all ranks together
     value = U * args.steps / (total_ms * 1e-3)
+    sweep_ms, march_ms = sampled_kernel_times(solver, stream, torch)
+    st1 = solver.stats()
 
     # ---- end-to-end leg: the same iteration with HOST buffers for what crosses the boundary every step ------------
     #   in : previous-iteration moments Tc, Tv from pinned host memory  (pbte_cuda_upload_moments)
     #   out: Tc, Qc, Tv, Qv and the residual back to host               (pbte_cuda_download_moments)
     # The flux is solver state and stays on the device, as in a Solve call of many iterations.
     block = P.ndof * P.ne
-    # pinned host buffers for everything that crosses the boundary (the C ABI takes plain host pointers)
     pin_m = torch.zeros((1 + P.dim) * block, dtype=torch.float64).pin_memory()   # [Tc | Qc] as the library holds them
     pin_c = torch.zeros((1 + P.dim) * P.ne, dtype=torch.float64).pin_memory()    # [Tv | Qv]
     hm, hcell = pin_m.numpy(), pin_c.numpy()
     host = {"Tc": hm[:block], "Qc": hm[block:].reshape(P.dim, block), "Tv": hcell[: P.ne], "Qv": hcell[P.ne:].reshape(P.dim, P.ne)}
     solver.download_moments(host)
-    barrier()
+    e2e_steps = min(args.steps, 50)
+    plumb.barrier()
     t0 = time.perf_counter()
     with torch.cuda.stream(stream):
-        for _ in range(args.steps):
+        for _ in range(e2e_steps):
             solver.upload_moments(host["Tc"], host["Tv"])   # previous iterate from host memory
-            res = step()
+            solver.iterate_async()
             solver.download_moments(host)                    # Tc, Qc, Tv, Qv back to host memory (synchronises)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
-    if dist is not None:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = U * args.steps / float(te.item())
+    plumb.barrier()
+    e2e_value = U * e2e_steps / plumb.max(time.perf_counter() - t0)
     h2d = (block + P.ne) * 8
     d2h = ((1 + P.dim) * block + (1 + P.dim) * P.ne + 1) * 8
 
@@ -389,7 +447,7 @@ def run_gpu(args, rank, world, local_rank):
             for _ in range(3):
                 g.sweep(); g.finish_iteration()
             ms = []
-            for _ in range(min(args.steps, 5)):
+            for _ in range(5):
                 g.sweep(); g.finish_iteration()
                 ms.append(g.stats().last_sweep_ms)
         gs = float(np.mean(ms)) * 1e-3
@@ -401,12 +459,14 @@ def run_gpu(args, rank, world, local_rank):
         solver.close()
         hs = pb.HostSolver(hc, 0)
         hs.solve(1)
+        iters_per_call = 20
         t0 = time.perf_counter()
-        _, iters, dev_ms = hs.solve(args.steps)
+        _, iters, loop_ms = hs.solve(iters_per_call)
         dt = time.perf_counter() - t0
-        solve_call = {"value": U * iters / dt, "unit": UNIT, "iterations_per_call": iters, "seconds": dt, "device_ms": dev_ms,
+        solve_call = {"value": U * iters / dt, "unit": UNIT, "iterations_per_call": iters, "seconds": dt, "iteration_loop_ms": loop_ms,
                       "h2d_bytes_per_call": P.ndir * P.nband * block * 8 + h2d, "d2h_bytes_per_call": P.ndir * P.nband * block * 8 + d2h,
-                      "note": "one Solve(coeff, macro) call on host DenseMatrix blocks: flux uploaded at entry and downloaded at exit (pageable memory)"}
+                      "note": "one PBTESolver::Solve(coeff, macro) call of the kept C++ API on host DenseMatrix blocks (views into the pinned slab that"
+                              " CreateInitialCoefficients hands out): the whole flux uploaded at entry and downloaded at exit as two bulk transfers"}
         hs.close()
 
     # ---- seconds to converged T (the second half of BASELINE.json's metric), N = 1 -------------------------------------
@@ -415,38 +475,52 @@ def run_gpu(args, rank, world, local_rank):
     # measured on the same mesh and quadrature with consistent face traces, to the reference's default tolerance 1e-8.
     converged = None
     if world == 1 and not strong:
+        t0 = time.perf_counter()
         hcc = pb.HostCase(wl["mesh"], wl["order"], wl["refine"], wl["angle_dim"], wl["polar"], azim, True, False, BC3, face_rule=1, num_spectral=wl["num_spectral"])
+        t1 = time.perf_counter()
         sc = pb.Solver(hcc.problem, device=local_rank, cache_policy=0, kernel=args.kernel)
         sc.build_schedule()
-        t0 = time.perf_counter()
+        t2 = time.perf_counter()
         try:
             iters, resid, _ = sc.solve(5000, 1e-8)
-            dt = time.perf_counter() - t0
+            dt = time.perf_counter() - t2
             converged = {"seconds": dt, "iterations": int(iters), "residual": float(resid), "tol": 1e-8, "updates_per_s": U * iters / dt,
-                         "what": "pbte_cuda_solve from zero initial state until |Tv - Tv_prev| / |Tv| < 1e-8; C2 mesh and quadrature, consistent face traces"
-                                 " (the reference's face rule diverges here)"}
+                         "face_rule": "consistent traces (the reference's own face rule, quirk Q1, diverges on this mesh)",
+                         "setup_seconds": {"host_mesh_and_element_matrices": t1 - t0, "device_image_schedule_operators": t2 - t1},
+                         "seconds_including_setup": time.perf_counter() - t0,
+                         "what": "pbte_cuda_solve from zero initial state until |Tv - Tv_prev| / |Tv| < 1e-8; C2 mesh and quadrature"}
         except pb.PbteError as ex:
             converged = {"error": str(ex)}
         sc.close()
         hcc.close()
+    if not strong:
+        solver.close()
+        hc.close()
+
+    # ---- strong scaling of the non-gray 3-D Si case at its full size, at every N ---------------------------------------
+    strong_rec = None
+    if not strong and not args.no_strong:
+        try:
+            strong_rec = strong_scaling_leg(args, plumb, pb, stream)
+        except Exception as ex:  # an extra must never take the headline down with it
+            strong_rec = {"workload": EXTRA_WORKLOADS["c3"]["label"], "error": f"{type(ex).__name__}: {ex}"}
 
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        plumb.close()
         return
 
     peaks, peak_src = load_measured_peaks()
     live = pb.measure_peaks(local_rank)
     U_rank = P.ndof * P.ne * (k1 - k0) * P.nband
-    sweep_s = float(np.mean(sweep_ms)) * 1e-3
+    sweep_s = sweep_ms * 1e-3
     fp64_peak = max(live["fp64_fma_tflops"], live["fp64_mma_tflops"])
     kernel_names = {1: "generic", 2: "warp-register", 3: "shared-operator marching"}
     if st1.kernel_used == 3:
         fin = mean_interior_inflow_faces(P, k0, k1)
         fpu = flops_per_update_shared(P.ndof, fin)
         kname = "sweep_march_regop_kernel" if st1.march_variant == 1 else "sweep_march_kernel"
-        kdesc = (f"{kname}<{P.ndof}> (one launch per step: one CTA per (direction, band) slot marching through {nlev} wavefront levels,"
-                 f" {st1.n_operator_classes} operator class(es), tile fill {st1.march_fill:.2f}), followed by moments_from_flux_kernel; sweep {sweep_s * 1e3:.3f} ms per step"
+        kdesc = (f"{kname}<{P.ndof}> (one launch per step: marching CTAs walk the {nlev} wavefront levels of every (direction, band) slot,"
+                 f" {st1.n_operator_classes} operator class(es), tile fill {st1.march_fill:.2f}), followed by iteration_tail_kernel; sweep + tail {sweep_s * 1e3:.3f} ms per step"
                  f" by CUDA events on the sweep stream; algorithmic flops = 2n(1+F_in)+2 = {fpu:.1f} per update with F_in = {fin:.3f} interior inflow"
                  f" faces per element (shared-operator algebra, DESIGN.md); the per-element LU algebra of the reference would be"
                  f" {flops_per_update(P.ndof, P.dim, P.nfaces):.0f} flop/update")
@@ -459,11 +533,10 @@ def run_gpu(args, rank, world, local_rank):
         sched = {"classes": nclass, "wavefront_levels": nlev, "kernel": kernel_names.get(st1.kernel_used, "?"), "cuda_graph": True,
                  "pivot_cache": "FullLU policy: pivot lanes cached, LU recomputed in registers"}
     # duration of the dominant kernel: the marching kernel alone (event recorded right behind it inside the sweep), else the sweep
-    march_s = float(np.mean(march_ms)) * 1e-3 if (st1.kernel_used == 3 and march_ms and min(march_ms) > 0.0) else 0.0
+    march_s = march_ms * 1e-3 if (st1.kernel_used == 3 and march_ms > 0.0) else 0.0
     kern_s = march_s if march_s > 0.0 else sweep_s
     achieved_tf = fpu * U_rank / kern_s / 1e12
     hbm_gbs = 16.0 * U_rank / kern_s / 1e9
-    launches = int(st1.kernel_launches - st0.kernel_launches)
     prof = os.path.join(ROOT, "profiles", "ncu_summary.json")
     traffic = None
     if os.path.exists(prof):
@@ -475,23 +548,24 @@ def run_gpu(args, rank, world, local_rank):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": (f"{wl['label']} ({k1 - k0} directions on this GPU), reference-compatible local matrices; {U} updates per step" if strong else
-                                f"C2: builtin unit-cube-hex refine 2 ({P.ne} hexes), DG order 2 (ndof {P.ndof}), 8 Gauss polar x {azim} uniform azimuth = {P.ndir} directions"
-                                f" ({k1 - k0} per GPU), gray SMRT = 2 bands, reference-compatible local matrices; {U} updates per step"),
-                   "parallelism": f"directions partitioned over {world} GPU(s), one FP64 all-reduce of [Tc|Qc] per step" if world > 1 else "single GPU",
+        "config": {"workload": (f"{wl['label']} ({k1 - k0} directions on this GPU), reference-compatible local matrices; {U} updates per step" if strong else WORKLOAD_NAME),
+                   "detail": f"{P.ne} elements, ndof {P.ndof}, {P.ndir} directions in all ({k1 - k0} per GPU), {P.nband} bands, reference-compatible local matrices; {U} updates per step",
+                   "parallelism": (f"directions partitioned over {world} GPU(s), one FP64 all-reduce of [Tc|Qc] per step issued by the library (NCCL)" if world > 1 else "single GPU"),
                    "l2_flush": f"none needed: the flux ({flux_mb:.0f} MB per GPU) is read and rewritten every step and exceeds the 126 MB L2",
                    "schedule": sched,
+                   "timed_region": f"{args.steps} iterations enqueued back to back (pbte_cuda_iterate_async), one synchronisation at the end: {total_ms:.1f} ms",
+                   "setup_seconds": {"host_mesh_and_element_matrices": host_setup_s, "device_image_schedule_operators": device_setup_s},
                    "residual_after_run": res},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "what": "per step: Tc,Tv uploaded from pinned host memory, sweep+finish through the C ABI, Tc,Qc,Tv,Qv,residual downloaded; flux stays device resident",
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "what": "per step: Tc,Tv uploaded from pinned host memory, one whole iteration through the C ABI, Tc,Qc,Tv,Qv,residual downloaded; flux stays device resident",
                 "solve_call": solve_call},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "pipe": "FP64 tensor pipe (DMMA m8n8k4), not bf16: peak measured live, MEASURED_PEAKS.json has no FP64 entry", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak, "traffic": traffic,
                      "kernel_ms": kern_s * 1e3, "sweep_ms": sweep_s * 1e3, "frac_of_whole_sweep": fpu * U_rank / sweep_s / 1e12 / fp64_peak,
                      "note": f"dominant kernel = {kdesc} x {U_rank} updates; achieved = algorithmic flops / {kern_s * 1e3:.3f} ms ("
-                             f"{'the marching kernel alone, CUDA event behind it' if march_s > 0.0 else 'the whole sweep'}); peak = FP64 pipe measured live by pbte_cuda_measure_peaks"
-                             f" (DFMA {live['fp64_fma_tflops']:.1f}, DMMA {live['fp64_mma_tflops']:.1f} TFLOP/s)",
+                             f"{'the marching kernel alone, CUDA event behind it, mean of 10 iterations sampled right after the timed region' if march_s > 0.0 else 'the whole sweep'}); peak = FP64 pipe measured live by pbte_cuda_measure_peaks"
+                             f" (DFMA {live['fp64_fma_tflops']:.1f}, DMMA {live['fp64_mma_tflops']:.1f} TFLOP/s; the two share one pipe: profiles/r02_fp64_mix_probe.txt)",
                      "hbm": {"achieved": hbm_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "frac": hbm_gbs / peaks.get("hbm_gbs"),
                              "algorithmic_bytes_per_update": 16, "peak_source": peak_src, "live_copy_gbs": live["hbm_copy_gbs"]}},
     }
@@ -499,25 +573,27 @@ def run_gpu(args, rank, world, local_rank):
         line["general_path"] = general
     if converged is not None:
         line["time_to_converged_T"] = converged
+    if strong_rec is not None:
+        line["strong_scaling"] = strong_rec
     if world == 1 and not args.no_cpu_baseline and not strong:
         try:
             line["cpu_baseline"] = cpu_baseline_leg()
         except Exception as ex:  # the CPU leg must never take the GPU numbers down with it
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
     print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    plumb.close()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=300, help="timed source iterations (300 x 0.45 ms: a timed region above 100 ms)")
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c2"] + sorted(EXTRA_WORKLOADS), help="c2 = the benchmark; c3/c4/c5 = extra full-size measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-general", action="store_true", help="skip the side measurement of the per-element LU kernel")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling record (full-size C3, directions split over the GPUs)")
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 warp-register, 3 shared-operator marching")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -530,7 +606,7 @@ def main():
         # convenience: re-launch under torchrun, one process per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", "29531", os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup),
-               "--kernel", str(args.kernel)]
+               "--kernel", str(args.kernel), "--workload", args.workload] + (["--no-strong"] if args.no_strong else [])
         sys.exit(subprocess.call(cmd))
     run_gpu(args, rank, world, local_rank)
 

@@ -142,6 +142,13 @@ struct pbte_handle
     static constexpr int kLookMax = 16;
     cudaEvent_t ev_iter[kLookMax] = {};           // one event per in-flight iteration of pbte_cuda_solve
 
+    // bulk transfer of all coefficient blocks (pbte_cuda_upload_coeff_all / download_coeff_all)
+    cudaStream_t xfer = nullptr;
+    cudaEvent_t ev_ready[2] = {}, ev_free[2] = {};
+    DevBuf<double> stage;               // two staging buffers of stage_blocks blocks each
+    DevBuf<int32_t> slot_of_block;      // [nloc * nband] flux slot of host block (k - k0) * nband + band
+    int stage_blocks = 0;
+
     // communication: one all-reduce of [Tc | Qc] per iteration, issued by the library when a communicator is attached
     ncclComm_t comm = nullptr;
     int comm_rank = 0, comm_size = 1;
@@ -174,6 +181,12 @@ struct pbte_handle
         for (cudaEvent_t e : ev_iter)
             if (e) cudaEventDestroy(e);
         if (h_hist) cudaFreeHost(h_hist);
+        for (int b = 0; b < 2; ++b)
+        {
+            if (ev_ready[b]) cudaEventDestroy(ev_ready[b]);
+            if (ev_free[b]) cudaEventDestroy(ev_free[b]);
+        }
+        if (xfer) cudaStreamDestroy(xfer);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (ev2) cudaEventDestroy(ev2);
@@ -222,6 +235,12 @@ int upload(DevBuf<T> &dst, const T *src, size_t count, cudaStream_t st)
     CK(dst.alloc(count));
     if (count) CK(cudaMemcpyAsync(dst.p, src, count * sizeof(T), cudaMemcpyHostToDevice, st));
     return PBTE_OK;
+}
+
+template <class T>
+int upload_vec(DevBuf<T> &dst, const T *src, size_t count, cudaStream_t st)
+{
+    return upload(dst, src, count, st);
 }
 
 DevProblem make_dev_problem(pbte_handle *h)
@@ -395,6 +414,86 @@ MarchKernelFn pick_regop_kernel(int n)
         case 64: return pick_regop_n<64>();
         default: return nullptr;
     }
+}
+
+// Coefficient blocks between the caller's layout (block j = (k - k0) * nband + band: ndof x ne column-major, contiguous) in a
+// staging buffer and the flux (slot-major, rows padded to np).  One thread per padded entry.
+template <bool UPLOAD>
+__global__ void __launch_bounds__(256) repack_blocks_kernel(int nblocks, int ne, int n, int np, const int32_t *__restrict__ slot_of_block, int j0,
+                                                           double *__restrict__ stage, double *__restrict__ flux)
+{
+    const size_t per = (size_t)ne * np, idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (idx >= (size_t)nblocks * per) return;
+    const int j = (int)(idx / per);
+    const size_t r = idx - (size_t)j * per, e = r / np;
+    const int i = (int)(r - e * np);
+    double *f = flux + (size_t)slot_of_block[j0 + j] * per + r;
+    double *sg = stage + ((size_t)j * ne + e) * n + i;
+    if (UPLOAD) *f = i < n ? *sg : 0.0;
+    else if (i < n) *sg = *f;
+}
+
+int transfer_all_blocks(pbte_handle *h, double *host, bool upload)
+{
+    const int nblk = h->nslots();
+    if (nblk == 0) return PBTE_OK;
+    const size_t block = (size_t)h->ne * h->n;
+    if (!h->xfer)
+    {
+        CK(cudaStreamCreateWithFlags(&h->xfer, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b)
+        {
+            CK(cudaEventCreateWithFlags(&h->ev_ready[b], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&h->ev_free[b], cudaEventDisableTiming));
+        }
+    }
+    if (h->slot_of_block.count != (size_t)nblk)
+    {
+        std::vector<int32_t> tbl(nblk);
+        for (int k = 0; k < h->nloc(); ++k)
+            for (int b = 0; b < h->nband; ++b) tbl[(size_t)k * h->nband + b] = h->slotdir_of_dir[k] * h->nband + b;
+        const int st = upload_vec(h->slot_of_block, tbl.data(), tbl.size(), h->stream);
+        if (st) return st;
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    if (h->stage_blocks == 0)
+    {
+        h->stage_blocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)nblk, ((size_t)32 << 20) / (block * sizeof(double))));
+        CK(h->stage.alloc(2 * (size_t)h->stage_blocks * block));
+    }
+    const int per = h->stage_blocks;
+    CK(cudaStreamSynchronize(h->stream));
+    int c = 0;
+    for (int j0 = 0; j0 < nblk; j0 += per, ++c)
+    {
+        const int b = c & 1, cnt = std::min(per, nblk - j0);
+        double *sg = h->stage.p + (size_t)b * per * block, *hp = host + (size_t)j0 * block;
+        const size_t bytes = (size_t)cnt * block * sizeof(double);
+        const unsigned grid = (unsigned)(((size_t)cnt * h->ne * h->np + 255) / 256);
+        if (upload)
+        {
+            if (c >= 2) CK(cudaStreamWaitEvent(h->xfer, h->ev_free[b], 0));
+            CK(cudaMemcpyAsync(sg, hp, bytes, cudaMemcpyHostToDevice, h->xfer));
+            CK(cudaEventRecord(h->ev_ready[b], h->xfer));
+            CK(cudaStreamWaitEvent(h->stream, h->ev_ready[b], 0));
+            repack_blocks_kernel<true><<<grid, 256, 0, h->stream>>>(cnt, h->ne, h->n, h->np, h->slot_of_block.p, j0, sg, h->flux.p);
+            CK(cudaEventRecord(h->ev_free[b], h->stream));
+        }
+        else
+        {
+            if (c >= 2) CK(cudaStreamWaitEvent(h->stream, h->ev_free[b], 0));
+            repack_blocks_kernel<false><<<grid, 256, 0, h->stream>>>(cnt, h->ne, h->n, h->np, h->slot_of_block.p, j0, sg, h->flux.p);
+            CK(cudaEventRecord(h->ev_ready[b], h->stream));
+            CK(cudaStreamWaitEvent(h->xfer, h->ev_ready[b], 0));
+            CK(cudaMemcpyAsync(hp, sg, bytes, cudaMemcpyDeviceToHost, h->xfer));
+            CK(cudaEventRecord(h->ev_free[b], h->xfer));
+        }
+        ++h->launches;
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaStreamSynchronize(h->xfer));
+    return PBTE_OK;
 }
 
 int check_handle(pbte_handle *h)
@@ -1313,6 +1412,49 @@ int pbte_cuda_download_coeff(pbte_handle_t *h, int32_t k, int32_t band, double *
     CK(cudaMemcpy2DAsync(host, n * sizeof(double), h->flux.p + (size_t)slot * h->ne * np, np * sizeof(double), n * sizeof(double), h->ne,
                          cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return PBTE_OK;
+}
+
+int pbte_cuda_upload_coeff_all(pbte_handle_t *h, const double *host)
+{
+    int st = check_handle(h);
+    if (st) return st;
+    int slot = 0;
+    if (h->nslots() > 0 && (st = coeff_slot(h, h->k0, 0, &slot))) return st;
+    if (!host) return fail(PBTE_ERR_INVALID, "null host pointer");
+    DeviceGuard guard(h->device);
+    return transfer_all_blocks(h, const_cast<double *>(host), true);
+}
+
+int pbte_cuda_download_coeff_all(pbte_handle_t *h, double *host)
+{
+    int st = check_handle(h);
+    if (st) return st;
+    int slot = 0;
+    if (h->nslots() > 0 && (st = coeff_slot(h, h->k0, 0, &slot))) return st;
+    if (!host) return fail(PBTE_ERR_INVALID, "null host pointer");
+    DeviceGuard guard(h->device);
+    return transfer_all_blocks(h, host, false);
+}
+
+int pbte_cuda_host_alloc(void **ptr, size_t bytes)
+{
+    if (!ptr) return fail(PBTE_ERR_INVALID, "null pointer");
+    *ptr = nullptr;
+    if (bytes == 0) return PBTE_OK;
+    const cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess)
+    {
+        (void)cudaGetLastError();
+        *ptr = nullptr;
+        return fail(e == cudaErrorMemoryAllocation ? PBTE_ERR_NOMEM : PBTE_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+    }
+    return PBTE_OK;
+}
+
+int pbte_cuda_host_free(void *ptr)
+{
+    if (ptr) cudaFreeHost(ptr);
     return PBTE_OK;
 }
 

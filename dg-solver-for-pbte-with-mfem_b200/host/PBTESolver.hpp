@@ -48,7 +48,8 @@ public:
         tol_ = tol;
         max_iter_ = max_iter;
     }
-    /// Device time of the sweeps of the last Solve (ms) and their count; DOF*angle*band updates per sweep.
+    /// Time the iteration loop of the last Solve took (ms, host clock around the loop: the iterations run back to back on the
+    /// device without host synchronisation) and its iteration count; DOF*angle*band updates per sweep.
     double LastSolveSweepMs() const { return sweep_ms_; }
     int LastSolveIterations() const { return iters_; }
     double UpdatesPerSweep() const { return static_cast<double>(ndof_) * ne_ * ndir_ * nbranch_ * nspec_; }
@@ -62,7 +63,13 @@ private:
     int max_iter_;
     int dim_ = 0, ndof_ = 0, ne_ = 0, nbranch_ = 0, nspec_ = 0, ndir_ = 0;
     int missing_attr_ = -1;
-    pbte_handle *dev_ = nullptr;
+    // One handle per device.  PBTE_DEVICES=0,1,.. (or "all") spreads the directions over several GPUs of this process: every handle
+    // owns a contiguous direction block, the library all-reduces [Tc | Qc] once per iteration (NCCL, include/pbte_cuda.h).
+    std::vector<pbte_handle *> devs_;
+    std::vector<int> dir_begin_;  // [devs_.size() + 1]
+    // Coefficient storage handed out by CreateInitialCoefficients: one pinned slab per call, [dir][branch][spec][ne][ndof], the
+    // blocks are views into it (mfem::DenseMatrix::UseExternalData).  Solve moves such a set with two bulk transfers.
+    mutable std::vector<void *> slabs_;
     double sweep_ms_ = 0.0;
     int iters_ = 0;
 };

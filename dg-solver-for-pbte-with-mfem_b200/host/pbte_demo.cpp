@@ -7,6 +7,7 @@
 #include "PBTESolver.hpp"
 #include "PhononProperties.hpp"
 #include "SpatialMesh.hpp"
+#include "Utils.hpp"
 
 #include <yaml-cpp/yaml.h>
 
@@ -118,6 +119,10 @@ int main(int argc, char *argv[])
                   << " DOF*angle*band updates/s" << std::endl;
         if (write_fields)
         {
+            // the dumps the reference's driver writes after the solve (src/PhononBTE.cpp:399-411)
+            utils::DumpCoefficients(coeff, quad, true);
+            utils::DumpTemperature(macro.Tc(), true);
+            utils::DumpElementIntegrals(element_data, true);
             macro.WriteParaView("pbte_fields");
             if (spatial.Mesh().SpaceDimension() == 2) macro.Write2DSliceTemperature("output/2D/results/T_slice.txt", 100, 100);
         }

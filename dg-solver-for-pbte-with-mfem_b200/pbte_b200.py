@@ -74,6 +74,7 @@ CUDA_ABI_SYMBOLS = [
     "pbte_cuda_macro_accumulate", "pbte_cuda_macro_finalize", "pbte_cuda_macro_residual", "pbte_cuda_get_stats",
     "pbte_cuda_get_stream", "pbte_cuda_measure_peaks", "pbte_cuda_iterate_async", "pbte_cuda_iterate_sync", "pbte_cuda_solve_ex",
     "pbte_cuda_comm_get_unique_id", "pbte_cuda_comm_attach", "pbte_cuda_comm_attach_all", "pbte_cuda_comm_detach",
+    "pbte_cuda_upload_coeff_all", "pbte_cuda_download_coeff_all", "pbte_cuda_host_alloc", "pbte_cuda_host_free",
 ]
 COMM_ID_BYTES = 128
 ITER_CALLBACK = C.CFUNCTYPE(None, C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_double)
@@ -117,6 +118,10 @@ def cuda_lib():
         lib.pbte_cuda_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         lib.pbte_cuda_get_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         lib.pbte_cuda_measure_peaks.argtypes = [C.c_int, c_double_p, c_double_p, c_double_p]
+        lib.pbte_cuda_upload_coeff_all.argtypes = [C.c_void_p, c_double_p]
+        lib.pbte_cuda_download_coeff_all.argtypes = [C.c_void_p, c_double_p]
+        lib.pbte_cuda_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+        lib.pbte_cuda_host_free.argtypes = [C.c_void_p]
         lib.pbte_cuda_iterate_async.argtypes = [C.c_void_p]
         lib.pbte_cuda_iterate_sync.argtypes = [C.c_void_p, C.POINTER(C.c_int64), c_double_p]
         lib.pbte_cuda_solve_ex.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_double, c_int32_p, c_double_p, c_double_p,
@@ -395,14 +400,24 @@ class Solver:
         _ck(self.lib.pbte_cuda_download_coeff(self._h, k, band, _dp(out)))
         return out
 
-    def download_all_coeff(self):
+    def download_all_coeff(self, per_block=False):
+        """All owned blocks [k1-k0][nband][ndof*ne]: one bulk call (pbte_cuda_download_coeff_all) or block by block."""
         p = self.problem
         k0, k1 = self.dir_range
         out = np.zeros((k1 - k0, p.nband, p.ndof * p.ne))
+        if not per_block:
+            _ck(self.lib.pbte_cuda_download_coeff_all(self._h, _dp(out)))
+            return out
         for k in range(k0, k1):
             for b in range(p.nband):
                 _ck(self.lib.pbte_cuda_download_coeff(self._h, k, b, _dp(out[k - k0, b])))
         return out
+
+    def upload_all_coeff(self, coeff):
+        coeff = np.ascontiguousarray(coeff, dtype=np.float64)
+        k0, k1 = self.dir_range
+        assert coeff.size == (k1 - k0) * self.problem.nband * self.problem.ndof * self.problem.ne
+        _ck(self.lib.pbte_cuda_upload_coeff_all(self._h, _dp(coeff)))
 
     def upload_moments(self, Tc=None, Tv=None):
         Tc = None if Tc is None else np.ascontiguousarray(Tc, dtype=np.float64)

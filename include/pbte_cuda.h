@@ -138,6 +138,14 @@ int pbte_cuda_reset_state(pbte_handle_t *h);
 /* One block coeff[k][band] as an (ndof x ne) column-major matrix, host memory. */
 int pbte_cuda_upload_coeff(pbte_handle_t *h, int32_t k, int32_t band, const double *host);
 int pbte_cuda_download_coeff(pbte_handle_t *h, int32_t k, int32_t band, double *host);
+/* All owned blocks in one call: host = [dir_end - dir_begin][nband][ndof*ne], direction-major, contiguous (the layout of
+ * PBTESolver::CreateInitialCoefficients here).  Contiguous transfers through a device staging buffer, padding and slot
+ * permutation on the device, copies overlapped with the repacking; full PCIe rate when `host` is pinned memory
+ * (pbte_cuda_host_alloc: cudaHostAlloc behind a plain-C call, so that the C++ host layer needs no CUDA headers). */
+int pbte_cuda_upload_coeff_all(pbte_handle_t *h, const double *host);
+int pbte_cuda_download_coeff_all(pbte_handle_t *h, double *host);
+int pbte_cuda_host_alloc(void **ptr, size_t bytes);
+int pbte_cuda_host_free(void *ptr);
 /* Previous-iteration moments used as the source of the next sweep (macro.Tc()/macro.Tv() on entry). */
 int pbte_cuda_upload_moments(pbte_handle_t *h, const double *Tc /*[ndof*ne]*/, const double *Tv /*[ne]*/);
 /* Tc [ndof*ne], Qc [dim][ndof*ne], Tv [ne], Qv [dim][ne]; any pointer may be NULL. */

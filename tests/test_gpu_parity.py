@@ -360,3 +360,84 @@ def test_graph_replay_equals_plain_launches_and_is_reproducible():
     assert np.array_equal(a["coeff"], b["coeff"]) and np.array_equal(a["Tc"], b["Tc"])
     assert np.array_equal(a["coeff"], c["coeff"]) and np.array_equal(a["Qc"], c["Qc"])  # bit-reproducible
     hc.close()
+
+
+def test_bulk_coefficient_transfer_equals_block_by_block():
+    """pbte_cuda_upload_coeff_all / download_coeff_all (staged bulk transfers, repacking on the device) against the per-block calls."""
+    hc = host_case("tet_p2")
+    P = hc.problem
+    rng = np.random.default_rng(11)
+    coeff = rng.standard_normal((P.ndir, P.nband, P.ndof * P.ne))
+    s = pb.Solver(P)
+    s.build_schedule()
+    s.upload_all_coeff(coeff)
+    assert np.array_equal(s.download_all_coeff(per_block=True), coeff)
+    assert np.array_equal(s.download_all_coeff(), coeff)
+    for k in (0, P.ndir - 1):
+        s.upload_coeff(k, 1, -coeff[k, 1])
+    back = s.download_all_coeff()
+    assert np.array_equal(back[0, 1], -coeff[0, 1]) and np.array_equal(back[1, 0], coeff[1, 0])
+    s.close()
+    # a handle that owns a direction block sees its own blocks only
+    k0, k1 = 3, 9
+    part = pb.Solver(P, dir_range=(k0, k1))
+    part.build_schedule()
+    part.upload_all_coeff(coeff[k0:k1])
+    assert np.array_equal(part.download_all_coeff(per_block=True), coeff[k0:k1])
+    part.close()
+    hc.close()
+
+
+@pytest.mark.parametrize("kernel", [0, 2, 1])
+def test_enqueued_iterations_equal_stepwise_iterations(kernel):
+    """pbte_cuda_iterate_async x 4 + one synchronisation (fused tail) == 4 x (sweep, finish_iteration): bit for bit."""
+    hc = host_case("quad_p2")
+    P = hc.problem
+    a = pb.Solver(P, kernel=kernel)
+    a.build_schedule()
+    for _ in range(4):
+        a.iterate_async()
+    n, res_a = a.iterate_sync()
+    assert n == 4
+    b = pb.Solver(P, kernel=kernel)
+    b.build_schedule()
+    for _ in range(4):
+        b.sweep()
+        res_b = b.finish_iteration()
+    ma, mb = a.download_moments(), b.download_moments()
+    assert res_a == res_b
+    for k in ("Tc", "Qc", "Tv", "Qv"):
+        assert np.array_equal(ma[k], mb[k]), k
+    assert np.array_equal(a.download_all_coeff(), b.download_all_coeff())
+    a.close()
+    b.close()
+    hc.close()
+
+
+@pytest.mark.parametrize("look", ["1", "8"])
+def test_device_stop_test_leaves_the_state_of_the_stopping_iteration(look, monkeypatch):
+    """pbte_cuda_solve keeps iterations in flight; the device raises the stop flag itself, so whatever was enqueued beyond the
+    stopping iteration must be a no-op: the state equals that of exactly `it` iterations, bit for bit (src/PBTESolver.cpp:327)."""
+    monkeypatch.setenv("PBTE_LOOKAHEAD", look)
+    hc = host_case("c1_tri_p1")
+    P = hc.problem
+    a = pb.Solver(P)
+    a.build_schedule()
+    it, res, hist = a.solve(200, 2e-2)
+    assert 2 < it < 200 and res < 2e-2 and (hist[:-1] >= 2e-2).all()
+    b = pb.Solver(P)
+    b.build_schedule()
+    it_b, res_b, hist_b = b.solve(it, 0.0)
+    assert it_b == it and res_b == res and np.array_equal(hist, hist_b)
+    ma, mb = a.download_moments(), b.download_moments()
+    for k in ("Tc", "Qc", "Tv", "Qv"):
+        assert np.array_equal(ma[k], mb[k]), k
+    assert np.array_equal(a.download_all_coeff(), b.download_all_coeff())
+    # the handle is usable afterwards: the stop flag does not outlive the solve
+    a.sweep()
+    r = a.finish_iteration()
+    b.sweep()
+    assert r == b.finish_iteration()
+    a.close()
+    b.close()
+    hc.close()
