@@ -1371,7 +1371,7 @@ int pbte_cuda_reset_state(pbte_handle_t *h)
         CK(cudaMemsetAsync(h->tc_prev.p, 0, h->tc_prev.count * sizeof(double), h->stream));
         CK(cudaMemsetAsync(h->error_flag.p, 0, sizeof(int32_t), h->stream));
     }
-    CK(cudaStreamSynchronize(h->stream));
+    // no wait: the memsets are ordered on the handle's stream like every later call
     return PBTE_OK;
 }
 

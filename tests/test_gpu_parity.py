@@ -421,10 +421,16 @@ def test_device_stop_test_leaves_the_state_of_the_stopping_iteration(look, monke
     monkeypatch.setenv("PBTE_LOOKAHEAD", look)
     hc = host_case("c1_tri_p1")
     P = hc.problem
+    probe = pb.Solver(P)
+    probe.build_schedule()
+    _, _, h0 = probe.solve(12, 0.0)
+    probe.close()
+    first_below = int(np.argmin(h0))  # the residual history is not monotone in general: stop at its first minimum
+    tol = float(np.nextafter(h0[:first_below].min(), 0.0)) if first_below > 0 else 2.0
     a = pb.Solver(P)
     a.build_schedule()
-    it, res, hist = a.solve(200, 2e-2)
-    assert 2 < it < 200 and res < 2e-2 and (hist[:-1] >= 2e-2).all()
+    it, res, hist = a.solve(200, tol)
+    assert 1 < it <= 12 and res < tol and (hist[:-1] >= tol).all()
     b = pb.Solver(P)
     b.build_schedule()
     it_b, res_b, hist_b = b.solve(it, 0.0)
