@@ -16,6 +16,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -117,8 +118,12 @@ struct pbte_handle
     bool march_regop = false;  // one operator class: operators in consumer registers (sweep_regop.cuh)
     int march_h_smem = 0;
     int march_ring = 0, march_nv = 0;  // tile-ring slots per CTA, staged vectors per slot
-    bool march_compact = false;        // operators stored compact (row-major n x n) instead of in MMA fragment order
+    int march_op_layout = 0;           // DevMarch::op_layout: 0 fragment pairs, 1 compact row-major, 2 split order
     int march_op_stride = 0;           // doubles per operator in m_ops
+    int march_max_op_cnt = 0, march_max_class_tiles = 0;
+    bool march_persist = false;             // sweep_march_kernel (persistent CTAs, work lists) instead of the one-CTA-per-slot classic kernel
+    int march_ncta = 0, march_npieces = 0;  // persistent CTAs of sweep_march_kernel and the pieces of their work lists
+    DevBuf<int32_t> m_cta_piece_begin, m_pieces, m_progress;
     size_t march_smem = 0;
     DevBuf<int32_t> m_slot_class, m_cls_level_begin, m_level_tile_begin, m_tile_oclass, m_tile_desc, m_cls_op_off, m_cls_op_cnt, m_oc_rep,
         m_oc_ksrc, m_oc_gsrc, m_cnbr;
@@ -338,7 +343,13 @@ DevMarch make_dev_march(pbte_handle *h)
     S.h_smem = h->march_h_smem;
     S.ring = h->march_ring;
     S.op_stride = h->march_op_stride;
-    S.op_compact = h->march_compact ? 1 : 0;
+    S.op_layout = h->march_op_layout;
+    S.max_op_cnt = h->march_max_op_cnt;
+    S.max_class_tiles = h->march_max_class_tiles;
+    S.ncta = h->march_ncta;
+    S.cta_piece_begin = h->m_cta_piece_begin.p;
+    S.pieces = h->m_pieces.p;
+    S.progress = h->m_progress.p;
     S.nv = h->march_nv;
     S.F = h->F;
     S.slot_class = h->m_slot_class.p;
@@ -389,6 +400,34 @@ MarchKernelFn pick_march_kernel(int n, bool stage)
         case 35: return pick_stage<35>(stage);
         case 36: return pick_stage<36>(stage);
         case 64: return pick_stage<64>(stage);
+        default: return nullptr;
+    }
+}
+
+template <int N>
+MarchKernelFn pick_classic_stage(bool stage)
+{
+    return stage ? sweep_march_classic_kernel<N, true> : sweep_march_classic_kernel<N, false>;
+}
+
+MarchKernelFn pick_classic_kernel(int n, bool stage)
+{
+    switch (n)
+    {
+        case 3: return pick_classic_stage<3>(stage);
+        case 4: return pick_classic_stage<4>(stage);
+        case 6: return pick_classic_stage<6>(stage);
+        case 8: return pick_classic_stage<8>(stage);
+        case 9: return pick_classic_stage<9>(stage);
+        case 10: return pick_classic_stage<10>(stage);
+        case 15: return pick_classic_stage<15>(stage);
+        case 16: return pick_classic_stage<16>(stage);
+        case 20: return pick_classic_stage<20>(stage);
+        case 25: return pick_classic_stage<25>(stage);
+        case 27: return pick_classic_stage<27>(stage);
+        case 35: return pick_classic_stage<35>(stage);
+        case 36: return pick_classic_stage<36>(stage);
+        case 64: return pick_classic_stage<64>(stage);
         default: return nullptr;
     }
 }
@@ -566,7 +605,8 @@ int enqueue_sweep(pbte_handle *h, int piv, bool fuse, int64_t *launch_count)
             CK(cudaMemsetAsync(h->m_trace.p, 0, cnt * sizeof(long long), h->stream));
             DevMarch St = make_dev_march(h);
             if (h->march_regop) pick_regop_kernel(h->n)<<<h->nslots(), regop_threads(h->n), h->march_smem, h->stream>>>(P, St);
-            else pick_march_kernel(h->n, h->march_stage)<<<h->nslots(), march_threads(h->n), h->march_smem, h->stream>>>(P, St);
+            else if (h->march_persist) pick_march_kernel(h->n, h->march_stage)<<<h->march_ncta, march_threads(h->n), h->march_smem, h->stream>>>(P, St);
+            else pick_classic_kernel(h->n, h->march_stage)<<<h->nslots(), march_threads(h->n), h->march_smem, h->stream>>>(P, St);
             std::vector<long long> host(cnt);
             CK(cudaMemcpyAsync(host.data(), h->m_trace.p, cnt * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
@@ -590,7 +630,8 @@ int enqueue_sweep(pbte_handle *h, int piv, bool fuse, int64_t *launch_count)
         else
 #endif
         if (h->march_regop) pick_regop_kernel(h->n)<<<h->nslots(), regop_threads(h->n), h->march_smem, h->stream>>>(P, S);
-        else pick_march_kernel(h->n, h->march_stage)<<<h->nslots(), march_threads(h->n), h->march_smem, h->stream>>>(P, S);
+        else if (h->march_persist) pick_march_kernel(h->n, h->march_stage)<<<h->march_ncta, march_threads(h->n), h->march_smem, h->stream>>>(P, S);
+        else pick_classic_kernel(h->n, h->march_stage)<<<h->nslots(), march_threads(h->n), h->march_smem, h->stream>>>(P, S);
         {
             // inside a stream capture the record must become an event-record NODE (external flag), else it is only a dependency
             cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -673,7 +714,7 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
     if (h->kernel_choice == 0 && sched.fill < 0.4) return PBTE_OK;
 
     // operator block layout per slot: for every operator class P, then Q_j of the class's inflow faces (ascending j)
-    const size_t FR = (size_t)frag_doubles(n);
+    const size_t FR = (size_t)frag_doubles(n), SP = (size_t)split_doubles(n);
     std::vector<int32_t> op_off((size_t)nclass * noc), op_cnt(nclass), slot_class(ns);
     for (int c = 0; c < nclass; ++c)
     {
@@ -722,7 +763,8 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
     // operators staged in shared memory when a slot's block fits (two CTAs per SM up to 100 KB each, one beyond)
     int max_optin = 0;
     CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
-    const size_t stage_bytes = (size_t)max_cnt * FR * sizeof(double);
+    h->march_max_op_cnt = max_cnt;
+    h->march_max_class_tiles = sched.max_class_tiles;
     // shared memory of a marching CTA: operators (staged when they fit) + metadata/barriers + tile ring.  Two CTAs per SM when
     // that leaves room for a ring of >= 6 tiles each, one CTA otherwise; without room for operators they are read through L1.
     h->march_nv = 2 + sched.max_inflow;
@@ -733,15 +775,26 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
     const size_t h_doubles = h->march_h_smem ? h_all : 0;
     const size_t slot_bytes = march_slot_bytes(n, sched.rows, h->march_nv, F);
     const size_t sm_total = (size_t)max_optin, sm_half = (228 * 1024) / 2 - 2048;
-    auto ring_for = [&](size_t budget, bool stage, int *ring) {
-        const size_t fixed = (stage ? stage_bytes : 0) + 64;
+    // Two kernels walk the tiles (sweep_shared.cuh): the persistent one cuts the slots into equal work lists, which pays when there are
+    // more slots than resident CTAs AND its operators are staged (measured, profiles/r02_kernel_probes.txt); otherwise the classic one.
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    bool persist = ns > (n <= 36 ? 2 : 1) * sms;
+    if (const char *ev = std::getenv("PBTE_MARCH_PERSIST")) persist = std::atoi(ev) != 0;
+    auto stage_bytes_of = [&](bool pers) { return (size_t)max_cnt * (pers ? SP : FR) * sizeof(double); };
+    auto meta_of = [&](bool pers, int r) {
+        return pers ? march_meta_bytes(noc, r, sched.max_class_tiles, h_doubles, march_wpt(n))
+                    : march_classic_meta_bytes(sched.max_levels, noc, r, sched.max_class_tiles, h_doubles);
+    };
+    auto ring_for = [&](bool pers, size_t budget, bool stage, int *ring) {
+        const size_t fixed = (stage ? stage_bytes_of(pers) : 0) + 64;
         // mbarrier parity waits are only valid within one phase of the barrier: a slot is always refilled by the same producer
         // warp (ring size a multiple of the producer warps per role: a warp works in order, so the slot's previous tile is loaded
         // before it waits for the slot again) and the ring holds at least one tile per consumer warp (a consumer must find the
         // slot of its next tile at most one phase behind).  A ring that breaks the first rule hangs on large meshes.
         const int step = march_role_warps(n) % 2 == 0 ? march_role_warps(n) : 2 * march_role_warps(n);
         for (int r = 16 / step * step; r >= march_min_ring(n) && r > 0; r -= step)
-            if (fixed + march_meta_bytes(sched.max_levels, noc, r, sched.max_class_tiles, h_doubles) + (size_t)r * slot_bytes <= budget)
+            if (fixed + meta_of(pers, r) + (size_t)r * slot_bytes <= budget)
             {
                 *ring = r;
                 return true;
@@ -757,7 +810,7 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
     h->march_regop = false;
     {
         int unused = 0;
-        bool want = !(allow_stage && ring_for(sm_half, true, &unused));
+        bool want = !(allow_stage && ring_for(false, sm_half, true, &unused));
         if (const char *ev = std::getenv("PBTE_MARCH_REGOP")) want = std::atoi(ev) != 0;
         if (want && noc == 1 && sched.max_inflow <= kRegMaxIn && pick_regop_kernel(n) != nullptr)
         {
@@ -772,6 +825,7 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
         }
     }
     MarchKernelFn fn = nullptr;
+    h->march_persist = false;
     if (h->march_regop)
     {
         h->march_stage = false;
@@ -780,20 +834,31 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
     }
     else
     {
-        if (allow_stage && ring_for(sm_half, true, &ring)) h->march_stage = true;
-        else if (allow_stage && ring_for(sm_total - 1024, true, &ring)) h->march_stage = true;
-        else if (ring_for(sm_half, false, &ring) || ring_for(sm_total - 1024, false, &ring)) h->march_stage = false;
-        else return fail(PBTE_ERR_INVALID, "marching kernel does not fit in shared memory for this ndof / level count");
-        h->march_smem = (h->march_stage ? stage_bytes : 0) + 64 + march_meta_bytes(sched.max_levels, noc, ring, sched.max_class_tiles, h_doubles) + (size_t)ring * slot_bytes;
-        fn = pick_march_kernel(n, h->march_stage);
+        auto configure = [&](bool pers) {
+            if (allow_stage && ring_for(pers, sm_half, true, &ring)) h->march_stage = true;
+            else if (allow_stage && ring_for(pers, sm_total - 1024, true, &ring)) h->march_stage = true;
+            else if (ring_for(pers, sm_half, false, &ring) || ring_for(pers, sm_total - 1024, false, &ring)) h->march_stage = false;
+            else return false;
+            return true;
+        };
+        if (!configure(persist)) return fail(PBTE_ERR_INVALID, "marching kernel does not fit in shared memory for this ndof / level count");
+        if (persist && !h->march_stage && !std::getenv("PBTE_MARCH_PERSIST"))
+        {
+            // operators from global memory: the classic kernel is the faster one
+            persist = false;
+            if (!configure(false)) return fail(PBTE_ERR_INVALID, "marching kernel does not fit in shared memory for this ndof / level count");
+        }
+        h->march_persist = persist;
+        h->march_smem = (h->march_stage ? stage_bytes_of(persist) : 0) + 64 + meta_of(persist, ring) + (size_t)ring * slot_bytes;
+        fn = persist ? pick_march_kernel(n, h->march_stage) : pick_classic_kernel(n, h->march_stage);
     }
     h->march_ring = ring;
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->march_smem));
     {
-        // operator storage: fragment order where a CTA stages its slot's block (or keeps it in registers), compact row-major where
-        // every tile reads its operators from global memory
-        h->march_compact = !h->march_stage && !h->march_regop;
-        h->march_op_stride = h->march_compact ? compact_doubles(n) : (int)FR;
+        // operator storage: split order where a persistent CTA stages its slot's block, fragment pairs where a classic CTA stages it or
+        // the consumers keep it in registers, compact row-major where every tile reads its operators from global memory
+        h->march_op_layout = h->march_regop ? 0 : (h->march_stage ? (h->march_persist ? 2 : 0) : 1);
+        h->march_op_stride = h->march_op_layout == 0 ? (int)FR : (h->march_op_layout == 2 ? (int)SP : compact_doubles(n));
         std::vector<unsigned long long> slot_base(ns);
         size_t total = 0;
         for (int s = 0; s < ns; ++s)
@@ -821,6 +886,70 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
         const int flag = *h->h_flag;
         CK(cudaMemsetAsync(h->error_flag.p, 0, sizeof(int32_t), h->stream));
         return fail(flag, "singular local system while building the shared operators");
+    }
+    // ---- work lists of the persistent marching CTAs (sweep_march_kernel) -------------------------------------------------------
+    // The tile sequences of all slots, laid end to end, are cut into equal shares, one per resident CTA; a CTA works through
+    // [head of its last slot] [whole slots] [tail of its first slot], so a tail always continues a head that another CTA started with.
+    if (h->march_persist)
+    {
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, march_threads(n), h->march_smem));
+        int resident = std::max(1, per_sm) * std::max(1, sms);
+        if (const char *ev = std::getenv("PBTE_MARCH_CTAS")) resident = std::max(1, std::atoi(ev));
+        // Cutting slots only pays when there are more slots than resident CTAs: the tiles of a slot depend on each other, so a slot
+        // takes the same time whoever processes its parts, and with every slot resident from the start (C2: 256 slots, 296 CTAs) the
+        // sweep already ends with the slowest slot (measured: 0.402 ms cut against 0.399 ms whole).  With more slots than CTAs the cut
+        // removes the partial last wave (C5 slice: 512 slots, 2.29 -> 2.04 ms; C3 slice 4.77 -> 4.28 ms).
+        bool split = (long long)ns > resident;
+        if (const char *ev = std::getenv("PBTE_MARCH_SPLIT")) split = std::atoi(ev) != 0;
+        std::vector<int32_t> slot_tiles(ns), tile_first(ns);
+        long long total = 0;
+        for (int sl = 0; sl < ns; ++sl)
+        {
+            const int c = slot_class[sl], lb = sched.cls_level_begin[c], le = sched.cls_level_begin[c + 1] - 1;
+            slot_tiles[sl] = sched.level_tile_begin[le] - sched.level_tile_begin[lb];
+            total += slot_tiles[sl];
+        }
+        const int ncta = split ? (int)std::min<long long>(resident, std::max<long long>(total, 1)) : ns;
+        std::vector<int32_t> cta_begin(ncta + 1, 0), pieces;
+        if (!split)
+            for (int sl = 0; sl < ns; ++sl)
+            {
+                cta_begin[sl + 1] = sl + 1;
+                pieces.insert(pieces.end(), {sl, 0, slot_tiles[sl], slot_tiles[sl]});
+            }
+        else
+        {
+            std::vector<long long> off(ns + 1, 0);
+            for (int sl = 0; sl < ns; ++sl) off[sl + 1] = off[sl] + slot_tiles[sl];
+            int s_lo = 0;
+            for (int j = 0; j < ncta; ++j)
+            {
+                const long long a = total * j / ncta, b = total * (j + 1) / ncta;
+                // slots intersecting [a, b)
+                while (s_lo < ns && off[s_lo + 1] <= a) ++s_lo;
+                std::vector<std::array<int32_t, 4>> mine;
+                for (int sl = s_lo; sl < ns && off[sl] < b; ++sl)
+                {
+                    const int t0 = (int)(std::max(a, off[sl]) - off[sl]), t1 = (int)(std::min(b, off[sl + 1]) - off[sl]);
+                    if (t1 > t0) mine.push_back({sl, t0, t1, slot_tiles[sl]});
+                }
+                // order: head of the last slot first (nothing to wait for), whole slots, the tail of the first slot last
+                std::stable_sort(mine.begin(), mine.end(), [](const std::array<int32_t, 4> &x, const std::array<int32_t, 4> &y) {
+                    auto rank = [](const std::array<int32_t, 4> &p) { return p[1] > 0 ? 2 : (p[2] < p[3] ? 0 : 1); };
+                    return rank(x) < rank(y);
+                });
+                for (const auto &pc : mine) pieces.insert(pieces.end(), pc.begin(), pc.end());
+                cta_begin[j + 1] = (int32_t)(pieces.size() / 4);
+            }
+        }
+        h->march_ncta = ncta;
+        h->march_npieces = (int)(pieces.size() / 4);
+        if ((st = upload(h->m_cta_piece_begin, cta_begin.data(), cta_begin.size(), h->stream))) return st;
+        if ((st = upload(h->m_pieces, pieces.data(), pieces.size(), h->stream))) return st;
+        CK(h->m_progress.alloc((size_t)std::max(ns, 1)));
+        CK(cudaMemsetAsync(h->m_progress.p, 0, h->m_progress.count * sizeof(int32_t), h->stream));
+        CK(cudaStreamSynchronize(h->stream));
     }
     // tail pass: enough slot chunks that the streaming CTAs fill the machine several times over
     {
@@ -1960,6 +2089,8 @@ int pbte_cuda_get_stats(pbte_handle_t *h, pbte_stats_t *s)
     s->march_fill = h->march_fill;
     s->march_variant = h->kernel_used == 3 && h->march_regop ? 1 : 0;
     s->operator_bytes = (int64_t)((h->m_ops.count + h->m_oph.count) * sizeof(double));
+    s->march_persistent = h->kernel_used == 3 && h->march_persist ? 1 : 0;
+    s->march_ctas = h->kernel_used == 3 ? (h->march_persist ? h->march_ncta : h->nslots()) : 0;
     return PBTE_OK;
 }
 

@@ -51,7 +51,8 @@ class Stats(C.Structure):
                 ("last_finish_ms", C.c_double), ("flux_bytes", C.c_int64), ("launches_per_sweep", C.c_int64),
                 ("kernel_used", C.c_int32), ("n_classes", C.c_int32), ("max_levels", C.c_int32),
                 ("n_operator_classes", C.c_int32), ("march_tiles", C.c_int32), ("march_variant", C.c_int32),
-                ("march_fill", C.c_double), ("operator_bytes", C.c_int64), ("last_march_ms", C.c_double)]
+                ("march_fill", C.c_double), ("operator_bytes", C.c_int64), ("last_march_ms", C.c_double),
+                ("march_persistent", C.c_int32), ("march_ctas", C.c_int32)]
 
 
 class HostSpec(C.Structure):

@@ -229,6 +229,8 @@ typedef struct pbte_stats
     double march_fill;        /* elements / (8 * tiles): occupancy of the MMA row blocks               */
     int64_t operator_bytes;   /* device bytes of the precomputed shared operators                      */
     double last_march_ms;     /* device time of the marching kernel alone inside the last sweep (0 = n/a) */
+    int32_t march_persistent; /* marching path: 1 = persistent CTAs with work lists (slots cut into equal shares), 0 = one CTA per slot */
+    int32_t march_ctas;       /* CTAs of the marching kernel */
 } pbte_stats_t;
 int pbte_cuda_get_stats(pbte_handle_t *h, pbte_stats_t *stats);
 /* The cudaStream_t the handle launches on (for CUDA-event timing by the caller). */

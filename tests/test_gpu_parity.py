@@ -447,3 +447,30 @@ def test_device_stop_test_leaves_the_state_of_the_stopping_iteration(look, monke
     a.close()
     b.close()
     hc.close()
+
+
+@pytest.mark.parametrize("name,nostage", [("c2_hex_p2_small", "0"), ("quad_p4", "0"), ("c0_default", "0"), ("tet_p2", "0"), ("tet_p2", "1"), ("hex_p3", "0"), ("tri_p3_si", "0")])
+@pytest.mark.parametrize("ctas", ["7", "0"])
+def test_persistent_marching_kernel_with_cut_slots(name, nostage, ctas, monkeypatch):
+    """The persistent marching kernel (work lists, slots cut into pieces that different CTAs hand on through global memory), forced on
+    small cases: PBTE_MARCH_CTAS=7 cuts every slot sequence into 7 shares, so most slots change hands; staged operators in split
+    order (ndof 25: one remainder column by DFMAs) and operators read from global memory (PBTE_MARCH_NOSTAGE=1)."""
+    monkeypatch.setenv("PBTE_MARCH_PERSIST", "1")
+    monkeypatch.setenv("PBTE_MARCH_REGOP", "0")
+    monkeypatch.setenv("PBTE_MARCH_NOSTAGE", nostage)
+    if ctas != "0":
+        monkeypatch.setenv("PBTE_MARCH_CTAS", ctas)
+        monkeypatch.setenv("PBTE_MARCH_SPLIT", "1")
+    hc = host_case(name)
+    P = hc.problem
+    iters = CASES[name]["iters"]
+    want = orc.solve(P, iters, 0.0, cache_lu=True, threads=8)
+    got = gpu_solve(P, iters, kernel=3)
+    st = got["stats"]
+    assert st.kernel_used == 3 and st.march_persistent == 1 and st.march_variant == 0
+    if ctas != "0":
+        assert st.march_ctas == min(7, st.march_tiles)
+    tol = tol_of(name, P)
+    for k in ("Tc", "Qc", "Tv", "Qv", "coeff"):
+        assert rel(got[k], want[k]) <= tol, (k, rel(got[k], want[k]))
+    hc.close()
