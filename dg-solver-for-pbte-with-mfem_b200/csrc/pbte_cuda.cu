@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <array>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -125,9 +126,14 @@ struct pbte_handle
     int march_ncta = 0, march_npieces = 0;  // persistent CTAs of sweep_march_kernel and the pieces of their work lists
     DevBuf<int32_t> m_cta_piece_begin, m_pieces, m_progress;
     size_t march_smem = 0;
-    DevBuf<int32_t> m_slot_class, m_cls_level_begin, m_level_tile_begin, m_tile_oclass, m_tile_desc, m_cls_op_off, m_cls_op_cnt, m_oc_rep,
-        m_oc_ksrc, m_oc_gsrc, m_cnbr;
-    DevBuf<uint8_t> m_cls_inmask, m_cface;
+    DevBuf<int32_t> m_slot_class, m_cls_level_begin, m_level_tile_begin, m_tile_oclass, m_tile_desc, m_cls_op_off, m_cls_op_cnt;
+    DevBuf<uint8_t> m_cls_inmask;
+    // local matrices of the operator-class representatives (all the marching path needs of the matrix image)
+    DevBuf<double> r_mass, r_massT, r_stiff, r_fmass, r_fcoup, r_fint, r_normal;
+    DevBuf<uint8_t> r_has_k, r_has_g, r_cface, r_present;
+    bool reps_only = false;      // the per-element matrix image was not uploaded: marching path only
+    int64_t image_bytes = 0;     // device bytes of local matrices held (per-element image and/or representatives)
+    double create_ms = 0.0;
     DevBuf<unsigned long long> m_slot_op_base;
     DevBuf<double> m_ops, m_oph, m_ctbc;
 
@@ -364,11 +370,17 @@ DevMarch make_dev_march(pbte_handle *h)
     S.ops = h->m_ops.p;
     S.oph = h->m_oph.p;
     S.ctbc = h->m_ctbc.p;
-    S.oc_rep = h->m_oc_rep.p;
-    S.oc_ksrc = h->m_oc_ksrc.p;
-    S.oc_gsrc = h->m_oc_gsrc.p;
-    S.cface = h->m_cface.p;
-    S.cnbr = h->m_cnbr.p;
+    S.rep_mass = h->r_mass.p;
+    S.rep_massT = h->r_massT.p;
+    S.rep_stiff = h->r_stiff.p;
+    S.rep_fmass = h->r_fmass.p;
+    S.rep_fcoup = h->r_fcoup.p;
+    S.rep_fint = h->r_fint.p;
+    S.rep_normal = h->r_normal.p;
+    S.rep_has_k = h->r_has_k.p;
+    S.rep_has_g = h->r_has_g.p;
+    S.rep_cface = h->r_cface.p;
+    S.rep_present = h->r_present.p;
     S.trace = h->m_trace.p;
     return S;
 }
@@ -453,6 +465,63 @@ MarchKernelFn pick_regop_kernel(int n)
         case 64: return pick_regop_n<64>();
         default: return nullptr;
     }
+}
+
+// Local matrices of the operator-class representatives, gathered from the caller's arrays (tens of elements at most): all that the
+// operator construction of the marching path reads (sweep_shared.cuh: build_operators_kernel).
+int upload_representatives(pbte_handle *h, const pbte_problem_t *p)
+{
+    const pbte_host::SharedPlan &plan = h->plan;
+    const int noc = plan.noclass, n = h->n, F = h->F, dim = h->dim;
+    const size_t nn = (size_t)n * n, ms = (size_t)h->ms;
+    std::vector<double> mass(noc * ms, 0.0), massT(noc * ms, 0.0), stiff((size_t)noc * dim * ms, 0.0), fmass((size_t)noc * F * ms, 0.0),
+        fcoup((size_t)noc * F * ms, 0.0), fint((size_t)noc * F * n, 0.0), normal((size_t)noc * F * 3, 0.0);
+    std::vector<uint8_t> has_k((size_t)noc * F, 0), has_g((size_t)noc * F, 0), cface((size_t)noc * F, 0), present((size_t)noc * F, 0);
+    for (int o = 0; o < noc; ++o)
+    {
+        const size_t e = (size_t)plan.oc_rep[o];
+        std::copy(p->mass + e * nn, p->mass + (e + 1) * nn, mass.begin() + o * ms);
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) massT[o * ms + i + (size_t)j * n] = p->mass[e * nn + j + (size_t)i * n];
+        for (int d = 0; d < dim; ++d) std::copy(p->stiff + (e * dim + d) * nn, p->stiff + (e * dim + d + 1) * nn, stiff.begin() + ((size_t)o * dim + d) * ms);
+        for (int f = 0; f < F; ++f)
+        {
+            std::copy(p->face_mass + (e * F + f) * nn, p->face_mass + (e * F + f + 1) * nn, fmass.begin() + ((size_t)o * F + f) * ms);
+            std::copy(p->face_normal + (e * F + f) * 3, p->face_normal + (e * F + f + 1) * 3, normal.begin() + ((size_t)o * F + f) * 3);
+        }
+        for (int j = 0; j < F; ++j)
+        {
+            const size_t oj = (size_t)o * F + j;
+            cface[oj] = plan.cface[e * F + j];
+            present[oj] = plan.cnbr[e * F + j] != PBTE_FACE_NONE;
+            const int ks = plan.oc_ksrc[oj], gs = plan.oc_gsrc[oj];
+            if (ks >= 0)
+            {
+                has_k[oj] = 1;
+                std::copy(p->face_coupling + (size_t)ks * nn, p->face_coupling + ((size_t)ks + 1) * nn, fcoup.begin() + oj * ms);
+            }
+            if (gs >= 0)
+            {
+                has_g[oj] = 1;
+                std::copy(p->face_integral + (size_t)gs * n, p->face_integral + ((size_t)gs + 1) * n, fint.begin() + oj * n);
+            }
+        }
+    }
+    int st;
+    if ((st = upload(h->r_mass, mass.data(), mass.size(), h->stream))) return st;
+    if ((st = upload(h->r_massT, massT.data(), massT.size(), h->stream))) return st;
+    if ((st = upload(h->r_stiff, stiff.data(), stiff.size(), h->stream))) return st;
+    if ((st = upload(h->r_fmass, fmass.data(), fmass.size(), h->stream))) return st;
+    if ((st = upload(h->r_fcoup, fcoup.data(), fcoup.size(), h->stream))) return st;
+    if ((st = upload(h->r_fint, fint.data(), fint.size(), h->stream))) return st;
+    if ((st = upload(h->r_normal, normal.data(), normal.size(), h->stream))) return st;
+    if ((st = upload(h->r_has_k, has_k.data(), has_k.size(), h->stream))) return st;
+    if ((st = upload(h->r_has_g, has_g.data(), has_g.size(), h->stream))) return st;
+    if ((st = upload(h->r_cface, cface.data(), cface.size(), h->stream))) return st;
+    if ((st = upload(h->r_present, present.data(), present.size(), h->stream))) return st;
+    CK(cudaStreamSynchronize(h->stream));  // the host vectors go out of scope
+    h->image_bytes += (int64_t)((mass.size() + massT.size() + stiff.size() + fmass.size() + fcoup.size() + fint.size() + normal.size()) * sizeof(double));
+    return PBTE_OK;
 }
 
 // Coefficient blocks between the caller's layout (block j = (k - k0) * nband + band: ndof x ne column-major, contiguous) in a
@@ -741,11 +810,6 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
     if ((st = upload(h->m_cls_inmask, sched.cls_inmask.data(), sched.cls_inmask.size(), h->stream))) return st;
     if ((st = upload(h->m_cls_op_off, op_off.data(), op_off.size(), h->stream))) return st;
     if ((st = upload(h->m_cls_op_cnt, op_cnt.data(), op_cnt.size(), h->stream))) return st;
-    if ((st = upload(h->m_oc_rep, plan.oc_rep.data(), plan.oc_rep.size(), h->stream))) return st;
-    if ((st = upload(h->m_oc_ksrc, plan.oc_ksrc.data(), plan.oc_ksrc.size(), h->stream))) return st;
-    if ((st = upload(h->m_oc_gsrc, plan.oc_gsrc.data(), plan.oc_gsrc.size(), h->stream))) return st;
-    if ((st = upload(h->m_cnbr, plan.cnbr.data(), plan.cnbr.size(), h->stream))) return st;
-    if ((st = upload(h->m_cface, plan.cface.data(), plan.cface.size(), h->stream))) return st;
     {
         // wall temperatures with rows padded to an even count (16-byte rows for the asynchronous copies)
         const int Fp = (F + 1) & ~1;
@@ -779,7 +843,7 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
     // more slots than resident CTAs AND its operators are staged (measured, profiles/r02_kernel_probes.txt); otherwise the classic one.
     int sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
-    bool persist = ns > (n <= 36 ? 2 : 1) * sms;
+    bool persist = ns > march_ctas_per_sm(n) * sms;
     if (const char *ev = std::getenv("PBTE_MARCH_PERSIST")) persist = std::atoi(ev) != 0;
     auto stage_bytes_of = [&](bool pers) { return (size_t)max_cnt * (pers ? SP : FR) * sizeof(double); };
     auto meta_of = [&](bool pers, int r) {
@@ -793,7 +857,8 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
         // before it waits for the slot again) and the ring holds at least one tile per consumer warp (a consumer must find the
         // slot of its next tile at most one phase behind).  A ring that breaks the first rule hangs on large meshes.
         const int step = march_role_warps(n) % 2 == 0 ? march_role_warps(n) : 2 * march_role_warps(n);
-        for (int r = 16 / step * step; r >= march_min_ring(n) && r > 0; r -= step)
+        const int cap = march_ctas_per_sm(n) == 1 ? 2 * march_consumers(n) + 8 : 16;  // deeper than that returns nothing
+        for (int r = cap / step * step; r >= march_min_ring(n) && r > 0; r -= step)
             if (fixed + meta_of(pers, r) + (size_t)r * slot_bytes <= budget)
             {
                 *ring = r;
@@ -835,9 +900,10 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
     else
     {
         auto configure = [&](bool pers) {
-            if (allow_stage && ring_for(pers, sm_half, true, &ring)) h->march_stage = true;
+            const size_t first = march_ctas_per_sm(n) == 1 ? sm_total - 1024 : sm_half;
+            if (allow_stage && ring_for(pers, first, true, &ring)) h->march_stage = true;
             else if (allow_stage && ring_for(pers, sm_total - 1024, true, &ring)) h->march_stage = true;
-            else if (ring_for(pers, sm_half, false, &ring) || ring_for(pers, sm_total - 1024, false, &ring)) h->march_stage = false;
+            else if (ring_for(pers, first, false, &ring) || ring_for(pers, sm_total - 1024, false, &ring)) h->march_stage = false;
             else return false;
             return true;
         };
@@ -1087,6 +1153,7 @@ int pbte_cuda_create(const pbte_problem_t *p, const pbte_options_t *opt_in, pbte
     pbte_options_t opt;
     if (opt_in) opt = *opt_in;
     else pbte_cuda_default_options(&opt);
+    const auto t_create = std::chrono::steady_clock::now();
 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -1171,26 +1238,44 @@ int pbte_cuda_create(const pbte_problem_t *p, const pbte_options_t *opt_in, pbte
         if (!(p->mass && p->stiff && p->face_mass && p->face_coupling && p->face_integral && p->face_tbc && h->has_topology && n > 0))
             return fail(PBTE_ERR_INVALID, "incomplete matrix set in problem image");
         int st;
-        if ((st = upload_matrices(h->mass, p->mass, ne, (int)n, h->ms, h->stream))) return st;
+        // operator classes for the shared-operator path (host side, from the caller's arrays)
+        if (h->kernel_choice == 0 || h->kernel_choice == 3) h->plan = pbte_host::classify_elements(*p, h->class_tol, h->max_classes);
+        // the marching path reads the local matrices of the class representatives only.  The per-element image
+        // ((2 + dim + 2F) n^2 doubles per element: 0.4 GB for C2, 17 GB for C4) is uploaded when a per-element kernel may run: kernel
+        // 1 / 2 requested, no operator classes found, or an image small enough that keeping the automatic choice open costs nothing
+        // (PBTE_IMAGE_LIMIT_MB, default 1024).  PBTE_IMAGE=full / reps forces either.  Without it kernel 0 means kernel 3.
+        const double full_mb = (double)(ne * (2 + p->dim + 2 * F) * n * n + ne * F * n) * sizeof(double) / 1048576.0;
+        double limit_mb = 1024.0;
+        if (const char *ev = std::getenv("PBTE_IMAGE_LIMIT_MB")) limit_mb = std::atof(ev);
+        bool reps = h->plan.ok && (h->kernel_choice == 3 || (h->kernel_choice == 0 && full_mb > limit_mb));
+        if (const char *ev = std::getenv("PBTE_IMAGE")) reps = h->plan.ok && h->kernel_choice != 1 && h->kernel_choice != 2 && std::string(ev) == "reps";
+        if (const char *ev = std::getenv("PBTE_IMAGE"))
+            if (std::string(ev) == "full") reps = false;
+        h->reps_only = reps;
+        if (h->plan.ok && (st = upload_representatives(h, p))) return st;
+        if (!reps)
         {
-            std::vector<double> mt(ne * n * n);
-            for (size_t e = 0; e < ne; ++e)
-                for (size_t i = 0; i < n; ++i)
-                    for (size_t j = 0; j < n; ++j) mt[e * n * n + i + j * n] = p->mass[e * n * n + j + i * n];
-            if ((st = upload_matrices(h->massT, mt.data(), ne, (int)n, h->ms, h->stream))) return st;
-            CK(cudaStreamSynchronize(h->stream));
+            if ((st = upload_matrices(h->mass, p->mass, ne, (int)n, h->ms, h->stream))) return st;
+            {
+                std::vector<double> mt(ne * n * n);
+                for (size_t e = 0; e < ne; ++e)
+                    for (size_t i = 0; i < n; ++i)
+                        for (size_t j = 0; j < n; ++j) mt[e * n * n + i + j * n] = p->mass[e * n * n + j + i * n];
+                if ((st = upload_matrices(h->massT, mt.data(), ne, (int)n, h->ms, h->stream))) return st;
+                CK(cudaStreamSynchronize(h->stream));
+            }
+            if ((st = upload_matrices(h->stiff, p->stiff, ne * p->dim, (int)n, h->ms, h->stream))) return st;
+            if ((st = upload_matrices(h->fmass, p->face_mass, ne * F, (int)n, h->ms, h->stream))) return st;
+            if ((st = upload_matrices(h->fcoup, p->face_coupling, ne * F, (int)n, h->ms, h->stream))) return st;
+            if ((st = upload(h->fint, p->face_integral, ne * F * n, h->stream))) return st;
+            h->image_bytes += (int64_t)((h->mass.count + h->massT.count + h->stiff.count + h->fmass.count + h->fcoup.count + h->fint.count) * sizeof(double));
         }
-        if ((st = upload_matrices(h->stiff, p->stiff, ne * p->dim, (int)n, h->ms, h->stream))) return st;
-        if ((st = upload_matrices(h->fmass, p->face_mass, ne * F, (int)n, h->ms, h->stream))) return st;
-        if ((st = upload_matrices(h->fcoup, p->face_coupling, ne * F, (int)n, h->ms, h->stream))) return st;
-        if ((st = upload(h->fint, p->face_integral, ne * F * n, h->stream))) return st;
+        else if (h->kernel_choice == 0) h->kernel_choice = 3;
         // a boundary face without a wall temperature (NaN) is reported when a sweep is requested
         if ((st = upload(h->ftbc, p->face_tbc, ne * F, h->stream))) return st;
         for (size_t i = 0; i < ne * F; ++i)
             if (p->face_nbr[i] == PBTE_FACE_BOUNDARY && std::isnan(p->face_tbc[i])) h->missing_bc = true;
         h->has_matrices = true;
-        // operator classes for the shared-operator path (host-side, needs the caller's arrays: done here)
-        if (h->kernel_choice == 0 || h->kernel_choice == 3) h->plan = pbte_host::classify_elements(*p, h->class_tol, h->max_classes);
     }
     if (p->basis_integrals && ne > 0 && n > 0)
     {
@@ -1210,6 +1295,7 @@ int pbte_cuda_create(const pbte_problem_t *p, const pbte_options_t *opt_in, pbte
         CK(cudaMemsetAsync(h->flux.p, 0, fl * sizeof(double), h->stream));
     }
     CK(cudaStreamSynchronize(h->stream));
+    h->create_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_create).count();
     cleanup.h = nullptr;
     *out = h;
     return PBTE_OK;
@@ -2089,6 +2175,9 @@ int pbte_cuda_get_stats(pbte_handle_t *h, pbte_stats_t *s)
     s->march_fill = h->march_fill;
     s->march_variant = h->kernel_used == 3 && h->march_regop ? 1 : 0;
     s->operator_bytes = (int64_t)((h->m_ops.count + h->m_oph.count) * sizeof(double));
+    s->image_bytes = h->image_bytes;
+    s->create_ms = h->create_ms;
+    s->image_reps_only = h->reps_only ? 1 : 0;
     s->march_persistent = h->kernel_used == 3 && h->march_persist ? 1 : 0;
     s->march_ctas = h->kernel_used == 3 ? (h->march_persist ? h->march_ncta : h->nslots()) : 0;
     return PBTE_OK;

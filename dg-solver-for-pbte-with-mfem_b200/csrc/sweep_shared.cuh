@@ -53,11 +53,17 @@ struct DevMarch
     double *ops;                      // operators in MMA fragment order
     double *oph;                      // [nslots][noclass][F][n] wall vectors h_f
     const double *ctbc;               // [ne][Fp] wall temperature per canonical face, Fp = F rounded up to even (16-byte rows)
-    // operator construction
-    const int32_t *oc_rep;            // [noclass]
-    const int32_t *oc_ksrc, *oc_gsrc; // [noclass][F] element*F + local face, or -1
-    const uint8_t *cface;             // [ne][F] canonical -> local face
-    const int32_t *cnbr;              // [ne][F] canonical face -> neighbour / PBTE_FACE_BOUNDARY / PBTE_FACE_NONE
+    // operator construction: the local matrices of the class representatives only (the marching path never needs the
+    // per-element matrix image; with pbte_options_t-independent PBTE_IMAGE=reps it is not even uploaded)
+    const double *rep_mass, *rep_massT;  // [noclass][ms]
+    const double *rep_stiff;             // [noclass][dim][ms]
+    const double *rep_fmass;             // [noclass][F][ms]   by LOCAL face of the representative
+    const double *rep_fcoup;             // [noclass][F][ms]   by CANONICAL face: K of an element of the class that has an interior face there
+    const double *rep_fint;              // [noclass][F][n]    by canonical face: g of an element of the class that has a wall there
+    const double *rep_normal;            // [noclass][F][3]    by local face
+    const uint8_t *rep_has_k, *rep_has_g;  // [noclass][F] the class has an interior / a wall face at canonical face j
+    const uint8_t *rep_cface;            // [noclass][F] canonical -> local face of the representative
+    const uint8_t *rep_present;          // [noclass][F] canonical face j exists
     long long *trace;                 // development builds (-DPBTE_TRACE) only: per-tile clock stamps of CTA 0, else null
 };
 
@@ -211,7 +217,6 @@ __global__ void __launch_bounds__(128) build_operators_kernel(DevProblem P, DevM
     __shared__ int s_fail;
     const int s = blockIdx.x, o = blockIdx.y;
     const int c = S.slot_class[s];
-    const int e = S.oc_rep[o];
     const unsigned inm = S.cls_inmask[(size_t)c * S.noclass + o];
     const size_t ms = P.ms;
     const double om[3] = {P.slot_dir[3 * s], P.slot_dir[3 * s + 1], P.slot_dir[3 * s + 2]};
@@ -223,21 +228,21 @@ __global__ void __launch_bounds__(128) build_operators_kernel(DevProblem P, DevM
         double a = 0.0;
         if (t < F)
         {
-            const int f = S.cface[(size_t)e * F + t];
-            if (S.cnbr[(size_t)e * F + t] != PBTE_FACE_NONE) a = dot_seq(P.fnormal + ((size_t)e * F + f) * 3, om, dim);
+            const int f = S.rep_cface[(size_t)o * F + t];
+            if (S.rep_present[(size_t)o * F + t]) a = dot_seq(S.rep_normal + ((size_t)o * F + f) * 3, om, dim);
         }
         s_af[t] = a;
     }
     if (t == 0) s_fail = 0;
     __syncthreads();
 
-    const double *Me = P.mass + (size_t)e * ms, *Ge = P.stiff + (size_t)e * dim * ms, *Fe = P.fmass + (size_t)e * F * ms;
+    const double *Me = S.rep_mass + (size_t)o * ms, *Ge = S.rep_stiff + (size_t)o * dim * ms, *Fe = S.rep_fmass + (size_t)o * F * ms;
     for (int idx = t; idx < n * n; idx += T)
     {
         double b = 0.0;
         for (int d = 0; d < dim; ++d) b = fma(-om[d], Ge[(size_t)d * ms + idx], b);
         for (int j = 0; j < F; ++j)
-            if (s_af[j] > 0.0) b = fma(s_af[j], Fe[(size_t)S.cface[(size_t)e * F + j] * ms + idx], b);
+            if (s_af[j] > 0.0) b = fma(s_af[j], Fe[(size_t)S.rep_cface[(size_t)o * F + j] * ms + idx], b);
         A[idx] = fma(v, b, P.nu_max * Me[idx]);
     }
     __syncthreads();
@@ -293,7 +298,7 @@ __global__ void __launch_bounds__(128) build_operators_kernel(DevProblem P, DevM
     };
     // P = A^-1 M^T
     {
-        const double *MTe = P.massT + (size_t)e * ms;
+        const double *MTe = S.rep_massT + (size_t)o * ms;
         for (int idx = t; idx < n * n; idx += T) R[idx] = MTe[idx];
         __syncthreads();
         lu_solve_columns(A, R, s_piv, n, n);
@@ -306,12 +311,12 @@ __global__ void __launch_bounds__(128) build_operators_kernel(DevProblem P, DevM
     {
         if (!(inm >> j & 1u)) continue;
         const double cin = 0.5 * v * (s_af[j] - fabs(s_af[j]));  // c_f (src/PBTESolver.cpp:282)
-        const int ks = S.oc_ksrc[(size_t)o * F + j], gs = S.oc_gsrc[(size_t)o * F + j];
+        const int ks = S.rep_has_k[(size_t)o * F + j] ? o * F + j : -1, gs = S.rep_has_g[(size_t)o * F + j] ? o * F + j : -1;
         double *out = ops + (size_t)m * OPS;
         if (ks >= 0)
         {
             // Q_j = -c_j A^-1 K_j
-            const double *K = P.fcoup + (size_t)ks * ms;
+            const double *K = S.rep_fcoup + (size_t)ks * ms;
             for (int idx = t; idx < n * n; idx += T) R[idx] = -cin * K[idx];
             __syncthreads();
             lu_solve_columns(A, R, s_piv, n, n);
@@ -324,7 +329,7 @@ __global__ void __launch_bounds__(128) build_operators_kernel(DevProblem P, DevM
         if (gs >= 0)
         {
             // h_j = -c_j (C/omega) A^-1 g_j
-            for (int i = t; i < n; i += T) R[i] = -cin * cb * P.fint[(size_t)gs * n + i];
+            for (int i = t; i < n; i += T) R[i] = -cin * cb * S.rep_fint[(size_t)gs * n + i];
             __syncthreads();
             lu_solve_columns(A, R, s_piv, n, 1);
             __syncthreads();
@@ -419,7 +424,14 @@ constexpr int kMaxIn = 4;          // inflow faces whose wall temperature a cons
 
 // MMA (consumer) warps of a marching CTA: two per SM sub-partition, so that one covers the other's descriptor / wall / store
 // phases; one per sub-partition for large elements (registers, and the ring must hold at least one tile per consumer)
-__host__ __device__ constexpr int march_consumers(int n) { return n <= 36 ? 8 : 4; }
+#ifndef PBTE_SMALL_CONSUMERS
+#define PBTE_SMALL_CONSUMERS 8
+#endif
+#ifndef PBTE_SMALL_CTAS
+#define PBTE_SMALL_CTAS 2
+#endif
+__host__ __device__ constexpr int march_consumers(int n) { return n <= 16 ? PBTE_SMALL_CONSUMERS : (n <= 36 ? 8 : 4); }
+__host__ __device__ constexpr int march_ctas_per_sm(int n) { return n <= 16 ? PBTE_SMALL_CTAS : (n <= 36 ? 2 : 1); }
 // Consumer warps that share one tile (compile-time experiment, off): with three or four MMA column blocks (ndof 25..36) two warps
 // split the columns — warp 0 the blocks 0 and 1, warp 1 the rest and the DFMA remainder — so a tile leaves its ring slot twice as
 // fast and the eight slots of a CTA hold four tiles in the MMAs and four on their way in.  Measured on C2 (profiles/r02_kernel_probes.txt):
@@ -501,7 +513,7 @@ __device__ __forceinline__ void st_release_gpu(int32_t *p, int v)
 //                     the ring and B fragments from the staged operators, remainder columns by DFMAs (Split<N>); releases
 //                     empty[slot]; adds wall terms, stores the tile with 16-byte stores, sets its bit in the bitmap (release).
 template <int N, bool STAGE>
-__global__ void __launch_bounds__(march_threads(N), N <= 36 ? 2 : 1) sweep_march_kernel(DevProblem P, DevMarch S)
+__global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_march_kernel(DevProblem P, DevMarch S)
 {
     constexpr int kConsumerWarps = march_consumers(N);
     constexpr int kSrcWarps = march_role_warps(N), kNbrWarps = march_role_warps(N);
@@ -1025,7 +1037,7 @@ __device__ __forceinline__ void classic_bulk_stage(void *dst, const void *src, u
 //                     fragments from the ring and B fragments from the staged operators; releases empty[slot]; adds wall
 //                     terms, stores the tile, sets its bit in the bitmap (release).
 template <int N, bool STAGE>
-__global__ void __launch_bounds__(march_threads(N), N <= 36 ? 2 : 1) sweep_march_classic_kernel(DevProblem P, DevMarch S)
+__global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_march_classic_kernel(DevProblem P, DevMarch S)
 {
     constexpr int kConsumerWarps = march_consumers(N);
     constexpr int kSrcWarps = march_role_warps(N), kNbrWarps = march_role_warps(N);

@@ -52,7 +52,8 @@ class Stats(C.Structure):
                 ("kernel_used", C.c_int32), ("n_classes", C.c_int32), ("max_levels", C.c_int32),
                 ("n_operator_classes", C.c_int32), ("march_tiles", C.c_int32), ("march_variant", C.c_int32),
                 ("march_fill", C.c_double), ("operator_bytes", C.c_int64), ("last_march_ms", C.c_double),
-                ("march_persistent", C.c_int32), ("march_ctas", C.c_int32)]
+                ("march_persistent", C.c_int32), ("march_ctas", C.c_int32), ("image_bytes", C.c_int64), ("create_ms", C.c_double),
+                ("image_reps_only", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class HostSpec(C.Structure):

@@ -117,7 +117,10 @@ int pbte_cuda_abi_version(void);
 const char *pbte_cuda_last_error(void);
 int pbte_cuda_device_count(int *count);
 void pbte_cuda_default_options(pbte_options_t *opt);
-/* Copies the problem image to the device (the caller may free its arrays afterwards). */
+/* Copies the problem image to the device (the caller may free its arrays afterwards).  Elements are grouped into operator
+ * classes here (host side); when the shared-operator marching path is certain to run (kernel = 3, or kernel = 0 on an image
+ * above PBTE_IMAGE_LIMIT_MB = 1024 MB with few classes) only the class representatives' local matrices go to the device
+ * instead of the per-element image (pbte_stats_t::image_bytes, image_reps_only; PBTE_IMAGE=full|reps forces). */
 int pbte_cuda_create(const pbte_problem_t *problem, const pbte_options_t *opt, pbte_handle_t **out);
 int pbte_cuda_destroy(pbte_handle_t *h);
 
@@ -231,6 +234,10 @@ typedef struct pbte_stats
     double last_march_ms;     /* device time of the marching kernel alone inside the last sweep (0 = n/a) */
     int32_t march_persistent; /* marching path: 1 = persistent CTAs with work lists (slots cut into equal shares), 0 = one CTA per slot */
     int32_t march_ctas;       /* CTAs of the marching kernel */
+    int64_t image_bytes;      /* device bytes of local matrices held: the per-element image and/or the class representatives */
+    double create_ms;         /* host time of pbte_cuda_create (classification + uploads) */
+    int32_t image_reps_only;  /* 1 = only the operator-class representatives' matrices were uploaded (marching path only) */
+    int32_t reserved0;
 } pbte_stats_t;
 int pbte_cuda_get_stats(pbte_handle_t *h, pbte_stats_t *stats);
 /* The cudaStream_t the handle launches on (for CUDA-event timing by the caller). */

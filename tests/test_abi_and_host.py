@@ -26,7 +26,7 @@ def test_struct_layouts_match_the_header():
     # sizes computed from the C declarations: 8 int32 + 9 pointers + ... (natural alignment)
     assert C.sizeof(pb.Problem) == 8 * 4 + 9 * 8 + 2 * 8 + 8 + 4 * 8 + 8
     assert C.sizeof(pb.Options) == 6 * 4 + 8 + 8 + 4 + 5 * 4
-    assert C.sizeof(pb.Stats) == 2 * 8 + 2 * 8 + 2 * 8 + 6 * 4 + 8 + 8 + 8 + 2 * 4
+    assert C.sizeof(pb.Stats) == 2 * 8 + 2 * 8 + 2 * 8 + 6 * 4 + 8 + 8 + 8 + 2 * 4 + 8 + 8 + 2 * 4
     assert pb.Options.class_tol.offset == 32 and pb.Stats.march_fill.offset == 72
 
 

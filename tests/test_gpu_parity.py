@@ -474,3 +474,26 @@ def test_persistent_marching_kernel_with_cut_slots(name, nostage, ctas, monkeypa
     for k in ("Tc", "Qc", "Tv", "Qv", "coeff"):
         assert rel(got[k], want[k]) <= tol, (k, rel(got[k], want[k]))
     hc.close()
+
+
+@pytest.mark.parametrize("name", ["c2_hex_p2_small", "tet_p2", "quad_p4", "c1_tri_p1"])
+def test_representatives_only_image_gives_identical_results(name, monkeypatch):
+    """the marching path builds its operators from the class representatives' matrices alone; with PBTE_IMAGE=reps the
+    per-element matrix image is not uploaded at all.  Same operators, so the same numbers bit for bit, from a fraction of the bytes."""
+    hc = host_case(name)
+    P = hc.problem
+    iters = CASES[name]["iters"]
+    monkeypatch.setenv("PBTE_IMAGE", "full")
+    full = gpu_solve(P, iters, kernel=0)
+    monkeypatch.setenv("PBTE_IMAGE", "reps")
+    reps = gpu_solve(P, iters, kernel=0)
+    assert full["stats"].image_reps_only == 0 and reps["stats"].image_reps_only == 1 and reps["stats"].kernel_used == 3
+    assert reps["stats"].image_bytes < full["stats"].image_bytes
+    if full["stats"].kernel_used == 3:
+        for k in ("Tc", "Qc", "Tv", "Qv", "coeff"):
+            assert np.array_equal(full[k], reps[k]), k
+    else:
+        for k in ("Tc", "Qc", "Tv", "Qv", "coeff"):
+            assert rel(full[k], reps[k]) <= tol_of(name, P), k
+    print(f"{name}: matrix image {full['stats'].image_bytes} -> {reps['stats'].image_bytes} bytes, create {full['stats'].create_ms:.2f} -> {reps['stats'].create_ms:.2f} ms")
+    hc.close()
