@@ -164,9 +164,11 @@ struct pbte_handle
     ncclComm_t comm = nullptr;
     int comm_rank = 0, comm_size = 1;
 
-    // graph replay of one sweep: [0] sweep + partial moments (the caller or NCCL reduces), [1] sweep + fused finish
-    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
-    int graph_mode[2] = {-1, -1};
+    // graph replay: [0] sweep + partial moments (the caller or NCCL reduces), [1] sweep + fused finish (whole single-GPU iteration),
+    // [2] sweep + NCCL all-reduce + finish (whole multi-GPU iteration of this rank)
+    cudaGraphExec_t graph_exec[3] = {nullptr, nullptr, nullptr};
+    int graph_mode[3] = {-1, -1, -1};
+    bool nccl_in_graph = true;
 
     // stats
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
@@ -177,7 +179,7 @@ struct pbte_handle
 
     void drop_graphs()
     {
-        for (int g = 0; g < 2; ++g)
+        for (int g = 0; g < 3; ++g)
         {
             if (graph_exec[g]) cudaGraphExecDestroy(graph_exec[g]);
             graph_exec[g] = nullptr;
@@ -1070,15 +1072,20 @@ int reset_ctrl(pbte_handle *h, double tol)
 
 // One whole source iteration, enqueued: sweep, all-reduce of [Tc | Qc] when a communicator is attached, finish.  No host
 // synchronisation; the iteration's history entry becomes valid when the stream reaches the end of the finish step.
-int graph_sweep(pbte_handle *h, bool fuse);
+int graph_sweep(pbte_handle *h, int mode);
 int enqueue_iteration(pbte_handle *h)
 {
     int st;
-    if (!h->comm) return graph_sweep(h, true);
-    if ((st = graph_sweep(h, false))) return st;
+    if (!h->comm) return graph_sweep(h, 1);
+    // one process per GPU: the rank's whole iteration (sweep, all-reduce, finish) replays as ONE graph; NCCL calls are capturable
+    if (h->use_graph && h->nccl_in_graph) return graph_sweep(h, 2);
+    if ((st = graph_sweep(h, 0))) return st;
     const ncclResult_t r = ncclAllReduce(h->mom_part.p, h->mom.p, h->mom.count, ncclDouble, ncclSum, h->comm, h->stream);
     if (r != ncclSuccess) return fail(PBTE_ERR_CUDA, std::string("ncclAllReduce: ") + ncclGetErrorString(r));
-    return enqueue_finish(h);
+    if ((st = enqueue_finish(h))) return st;
+    CK(cudaEventRecord(h->ev2, h->stream));
+    ++h->iter_enq;
+    return PBTE_OK;
 }
 
 // Waits for history entry `index` (an event recorded behind its finish step) and decodes it.
@@ -1186,6 +1193,7 @@ int pbte_cuda_create(const pbte_problem_t *p, const pbte_options_t *opt_in, pbte
     h->cache_policy = opt.cache_policy;
     h->kernel_choice = opt.kernel;
     h->use_graph = opt.use_graph;
+    if (const char *ev = std::getenv("PBTE_NCCL_GRAPH")) h->nccl_in_graph = std::atoi(ev) != 0;
     if (opt.class_tol > 0.0) h->class_tol = opt.class_tol;
     if (opt.max_classes > 0) h->max_classes = opt.max_classes;
     if (opt.kernel < 0 || opt.kernel > 3) return fail(PBTE_ERR_INVALID, "unknown kernel choice");
@@ -1733,7 +1741,10 @@ int check_sweep_ready(pbte_handle *h)
 }
 
 // One sweep (and its tail) on the handle's stream, replayed as a CUDA graph where possible.
-int graph_sweep(pbte_handle *h, bool fuse)
+// One sweep (and what follows it) on the handle's stream, replayed as a CUDA graph where possible.
+//   mode 0: sweep + partial moment vector; 1: sweep + fused finish (a whole single-GPU iteration); 2: sweep + NCCL all-reduce of the
+//   moment vector + finish (a whole iteration of one rank of a multi-GPU run).
+int graph_sweep(pbte_handle *h, int mode)
 {
     int st;
     int piv = 0;
@@ -1744,7 +1755,17 @@ int graph_sweep(pbte_handle *h, bool fuse)
 #ifdef PBTE_TRACE
     if (std::getenv("PBTE_TRACE_FILE")) graph_ok = false;  // the traced sweep synchronises and writes a file
 #endif
-    const int g = fuse ? 1 : 0;
+    auto enqueue_all = [&]() -> int {
+        int rc = enqueue_sweep(h, piv, mode == 1, &launches);
+        if (rc || mode != 2) return rc;
+        const ncclResult_t r = ncclAllReduce(h->mom_part.p, h->mom.p, h->mom.count, ncclDouble, ncclSum, h->comm, h->stream);
+        if (r != ncclSuccess) return fail(PBTE_ERR_CUDA, std::string("ncclAllReduce: ") + ncclGetErrorString(r));
+        ++launches;
+        if ((rc = enqueue_finish(h))) return rc;
+        ++launches;
+        return PBTE_OK;
+    };
+    const int g = mode;
     if (graph_ok && (!h->graph_exec[g] || h->graph_mode[g] != piv))
     {
         if (h->graph_exec[g])
@@ -1753,19 +1774,23 @@ int graph_sweep(pbte_handle *h, bool fuse)
             h->graph_exec[g] = nullptr;
         }
         cudaGraph_t graph = nullptr;
+        const int64_t launches_before = h->launches;
         CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-        st = enqueue_sweep(h, piv, fuse, &launches);
+        st = enqueue_all();
         const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+        h->launches = launches_before;  // nothing ran during the capture
         cudaError_t ie = cudaSuccess;
         if (st == PBTE_OK && ce == cudaSuccess) ie = cudaGraphInstantiate(&h->graph_exec[g], graph, 0);
         if (graph) cudaGraphDestroy(graph);
         if (st != PBTE_OK || ce != cudaSuccess || ie != cudaSuccess)
         {
-            // capture or instantiation failed: this handle goes on with plain launches
+            // capture or instantiation failed: this handle goes on with plain launches (a graph with an NCCL node: without NCCL in it)
             (void)cudaGetLastError();
             h->graph_exec[g] = nullptr;
-            h->use_graph = 0;
+            if (mode == 2) h->nccl_in_graph = false;
+            else h->use_graph = 0;
             graph_ok = false;
+            if (mode == 2) return enqueue_iteration(h);
         }
         else
         {
@@ -1782,15 +1807,18 @@ int graph_sweep(pbte_handle *h, bool fuse)
     }
     else
     {
-        if ((st = enqueue_sweep(h, piv, fuse, &launches))) return st;
+        launches = 0;
+        const int64_t launches_before = h->launches;
+        if ((st = enqueue_all())) return st;
+        h->launches = launches_before;
         h->launches_per_sweep = launches;
     }
     CK(cudaEventRecord(h->ev1, h->stream));
-    if (fuse) CK(cudaEventRecord(h->ev2, h->stream));
+    if (mode != 0) CK(cudaEventRecord(h->ev2, h->stream));
     h->sweep_timed = true;
     h->launches += launches;
     ++h->sweeps;
-    if (fuse) ++h->iter_enq;
+    if (mode != 0) ++h->iter_enq;
     if (piv == 1) h->pivots_recorded = true;
     return PBTE_OK;
 }
@@ -1828,7 +1856,7 @@ int solve_handles(pbte_handle **hs, int nh, int32_t max_iter, double tol, int32_
                 for (int i = 0; i < nh && st == PBTE_OK; ++i)
                 {
                     DeviceGuard guard(hs[i]->device);
-                    st = graph_sweep(hs[i], false);
+                    st = graph_sweep(hs[i], 0);
                 }
                 if (st) break;
                 ncclGroupStart();
@@ -1853,11 +1881,6 @@ int solve_handles(pbte_handle **hs, int nh, int32_t max_iter, double tol, int32_
             {
                 DeviceGuard guard(hs[0]->device);
                 st = enqueue_iteration(hs[0]);
-                if (st == PBTE_OK && hs[0]->comm)
-                {
-                    if (cudaEventRecord(hs[0]->ev2, hs[0]->stream) != cudaSuccess) st = fail(PBTE_ERR_CUDA, "cudaEventRecord failed");
-                    ++hs[0]->iter_enq;
-                }
             }
             if (st) break;
             {
@@ -1904,7 +1927,7 @@ int pbte_cuda_sweep(pbte_handle_t *h)
     if (st) return st;
     if ((st = check_sweep_ready(h))) return st;
     DeviceGuard guard(h->device);
-    return graph_sweep(h, false);
+    return graph_sweep(h, 0);
 }
 
 int pbte_cuda_moment_buffer(pbte_handle_t *h, double **device_ptr, size_t *count)
@@ -1945,13 +1968,7 @@ int pbte_cuda_iterate_async(pbte_handle_t *h)
     if ((st = check_sweep_ready(h))) return st;
     if (!h->has_basis) return fail(PBTE_ERR_STATE, "iterate needs basis_integrals in the problem image");
     DeviceGuard guard(h->device);
-    if ((st = enqueue_iteration(h))) return st;
-    if (h->comm)
-    {
-        CK(cudaEventRecord(h->ev2, h->stream));
-        ++h->iter_enq;
-    }
-    return PBTE_OK;
+    return enqueue_iteration(h);
 }
 
 int pbte_cuda_iterate_sync(pbte_handle_t *h, int64_t *iterations, double *residual)

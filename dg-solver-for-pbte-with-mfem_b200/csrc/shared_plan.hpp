@@ -20,7 +20,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <map>
+#include <queue>
 #include <string>
 #include <vector>
 
@@ -280,9 +282,163 @@ struct MarchSchedule
     double fill = 0.0;                     // elements / (8 * tiles)
 };
 
+// Tiles by list scheduling instead of level by level (build_march_schedule, default): a wavefront level of a DAG class rarely holds
+// a multiple of 8 elements of each operator class (tetrahedra: 72 classes, ~18 elements per (level, class) at full C3 size and half
+// that on a GPU's slice: tiles 52 - 78 % full), and a half-empty tile costs the marching kernel what a full one costs.  An element
+// may go into any tile behind the tiles of its upwind neighbours, so tiles are filled across levels: an element becomes ELIGIBLE
+// kTileDelay tiles after the last tile of its upwind neighbours (the marching CTA has that many tiles in flight: a tile whose
+// prerequisite was emitted just before it would stall the pipeline), and the next tile is taken from the operator class with eight
+// eligible elements whose oldest one has waited longest; without a full class, from the class of the oldest eligible element, and
+// with nothing eligible from the element that becomes eligible first.  Every DAG class becomes one "level" of the tables.
+// Measured on a B200 (profiles/r02_kernel_probes.txt, run h): tetrahedra (C3 slice) 3.78 -> 2.93 ms per sweep at a delay of 8 tiles
+// (fill 0.52 -> 0.71; delay 0 fills to 0.80 and takes 7.8 ms: every other tile waits for its predecessor; 4: 3.68, 16: 3.08); Cartesian
+// hexes / quads, whose level tiles are 95 % full already, lose 2 - 4 % to the tighter dependencies.  So the level schedule stays where it
+// fills its tiles to kMergeBelowFill and list scheduling takes over below (PBTE_TILE_MERGE=0/1 forces one).
+constexpr int kTileDelay = 8;
+constexpr double kMergeBelowFill = 0.85;
+
+inline void schedule_class_merged(const SharedPlan &plan, const int32_t *lv, const uint8_t *mi, const uint8_t *mb, const uint8_t *inm,
+                                  std::vector<int32_t> &tile_desc, std::vector<int32_t> &tile_oclass, int &ntiles, int rows, int delay)
+{
+    const int ne = plan.ne, F = plan.F, noc = plan.noclass;
+    const int t_begin = ntiles;
+    // downwind adjacency (reverse edges) and the number of upwind neighbours not yet placed
+    std::vector<int32_t> indeg(ne, 0), down_begin(ne + 1, 0), down;
+    for (int e = 0; e < ne; ++e)
+        for (int j = 0; j < F; ++j)
+        {
+            const size_t cs = (size_t)e * F + j;
+            if (plan.cnbr[cs] >= 0 && (mi[e] >> plan.cface[cs] & 1u))
+            {
+                ++indeg[e];
+                ++down_begin[plan.cnbr[cs] + 1];
+            }
+        }
+    for (int e = 0; e < ne; ++e) down_begin[e + 1] += down_begin[e];
+    down.resize(down_begin[ne]);
+    {
+        std::vector<int32_t> cur(down_begin.begin(), down_begin.end() - 1);
+        for (int e = 0; e < ne; ++e)
+            for (int j = 0; j < F; ++j)
+            {
+                const size_t cs = (size_t)e * F + j;
+                if (plan.cnbr[cs] >= 0 && (mi[e] >> plan.cface[cs] & 1u)) down[cur[plan.cnbr[cs]]++] = e;
+            }
+    }
+    // per operator class: elements waiting for their eligibility tile (min-heap on that tile), and eligible ones (oldest first)
+    typedef std::pair<int64_t, int32_t> Key;  // (tile index or age key, element)
+    std::vector<std::priority_queue<Key, std::vector<Key>, std::greater<Key>>> waiting(noc), eligible(noc);
+    std::vector<int32_t> tile_of(ne, -1), last_dep(ne, -1);
+    auto release = [&](int e) {  // all upwind neighbours of e are placed
+        const int64_t at = last_dep[e] < 0 ? 0 : (int64_t)last_dep[e] + 1 + delay;
+        waiting[plan.elem_oclass[e]].push({at, e});
+    };
+    for (int e = 0; e < ne; ++e)
+        if (indeg[e] == 0) release(e);
+    int placed = 0;
+    std::vector<int32_t> members;
+    while (placed < ne)
+    {
+        const int t = ntiles - t_begin;  // index in class of the tile being formed
+        int best = -1, best_full = -1;
+        int64_t oldest = INT64_MAX, oldest_full = INT64_MAX, soonest = INT64_MAX;
+        int soon_class = -1;
+        for (int o = 0; o < noc; ++o)
+        {
+            while (!waiting[o].empty() && waiting[o].top().first <= t)
+            {
+                const Key k = waiting[o].top();
+                waiting[o].pop();
+                // age key: wavefront level first (keeps the front compact), then the tile it became eligible at
+                eligible[o].push({((int64_t)lv[k.second] << 32) | (int64_t)(uint32_t)k.first, k.second});
+            }
+            if (!eligible[o].empty())
+            {
+                const int64_t age = eligible[o].top().first;
+                if (age < oldest) oldest = age, best = o;
+                if ((int)eligible[o].size() >= kTileElems && age < oldest_full) oldest_full = age, best_full = o;
+            }
+            if (!waiting[o].empty() && waiting[o].top().first < soonest) soonest = waiting[o].top().first, soon_class = o;
+        }
+        const int o = best_full >= 0 ? best_full : (best >= 0 ? best : soon_class);
+        members.clear();
+        while ((int)members.size() < kTileElems && !eligible[o].empty())
+        {
+            members.push_back(eligible[o].top().second);
+            eligible[o].pop();
+        }
+        if (members.empty())
+        {
+            // nothing eligible anywhere: the elements of this class that become eligible first go now
+            while ((int)members.size() < kTileElems && !waiting[o].empty())
+            {
+                members.push_back(waiting[o].top().second);
+                waiting[o].pop();
+            }
+        }
+        const size_t base = tile_desc.size();
+        tile_desc.resize(base + (size_t)rows * kTileElems, kSrcSkip);
+        tile_oclass.push_back(o);
+        int32_t *hdr = tile_desc.data() + base + (size_t)(1 + F) * kTileElems;
+        for (int k = 0; k < kTileElems; ++k) hdr[k] = 0;
+        hdr[0] = o;
+        hdr[1] = 0;
+        hdr[2] = t;
+        int dep = -1;
+        for (size_t cnt = 0; cnt < members.size(); ++cnt)
+        {
+            const int e = members[cnt];
+            tile_desc[base + cnt] = e;
+            int m = 0;
+            for (unsigned rest = inm[o]; rest; rest &= rest - 1, ++m)
+            {
+                const int j = __builtin_ctz(rest);
+                const size_t cs = (size_t)e * F + j;
+                const int f = plan.cface[cs];
+                int32_t code = kSrcSkip;
+                if (plan.cnbr[cs] >= 0 && (mi[e] >> f & 1u)) code = plan.cnbr[cs];
+                else if (plan.cnbr[cs] == PBTE_FACE_BOUNDARY && (mb[e] >> f & 1u)) code = kSrcWall;
+                tile_desc[base + (size_t)(1 + m) * kTileElems + cnt] = code;
+                if (code >= 0) dep = std::max(dep, (int)tile_of[code]);
+            }
+        }
+        tile_desc[base + (size_t)(1 + F) * kTileElems + 3] = dep;
+        for (int e : members)
+        {
+            tile_of[e] = t;
+            for (int k = down_begin[e]; k < down_begin[e + 1]; ++k)
+            {
+                const int d = down[k];
+                last_dep[d] = std::max(last_dep[d], (int32_t)t);
+                if (--indeg[d] == 0) release(d);
+            }
+        }
+        placed += (int)members.size();
+        ++ntiles;
+    }
+}
+
+inline MarchSchedule build_march_schedule_mode(const SharedPlan &plan, int nclass, const int32_t *level, const uint8_t *cin, const uint8_t *cbin, int mode);
+
 // level [nclass][ne], cin / cbin [nclass][ne]: bit f (LOCAL face) = interior / wall inflow face of the class
 inline MarchSchedule build_march_schedule(const SharedPlan &plan, int nclass, const int32_t *level, const uint8_t *cin, const uint8_t *cbin)
 {
+    return build_march_schedule_mode(plan, nclass, level, cin, cbin, -1);
+}
+
+// mode: 0 one wavefront level at a time, 1 list scheduling across levels, -1 level schedule unless its tiles are too empty
+inline MarchSchedule build_march_schedule_mode(const SharedPlan &plan, int nclass, const int32_t *level, const uint8_t *cin, const uint8_t *cbin, int mode)
+{
+    if (const char *ev = std::getenv("PBTE_TILE_MERGE")) mode = std::atoi(ev) != 0 ? 1 : 0;
+    if (mode < 0)
+    {
+        MarchSchedule by_level = build_march_schedule_mode(plan, nclass, level, cin, cbin, 0);
+        if (by_level.fill >= kMergeBelowFill || std::getenv("PBTE_TILE_MERGE")) return by_level;
+        return build_march_schedule_mode(plan, nclass, level, cin, cbin, 1);
+    }
+    const bool merge = mode == 1;
+    int delay = kTileDelay;
+    if (const char *ev = std::getenv("PBTE_TILE_DELAY")) delay = std::max(0, std::atoi(ev));
     MarchSchedule S;
     const int ne = plan.ne, F = plan.F;
     S.nclass = nclass;
@@ -310,6 +466,19 @@ inline MarchSchedule build_march_schedule(const SharedPlan &plan, int nclass, co
             }
             inm[o] = (uint8_t)m;
             S.max_inflow = std::max(S.max_inflow, (int)__builtin_popcount(m));
+        }
+        if (merge)
+        {
+            // every element's upwind neighbours must lie in earlier tiles: tiles across levels (schedule_class_merged)
+            S.max_levels = std::max(S.max_levels, 1);
+            S.cls_level_begin[c + 1] = S.cls_level_begin[c] + 2;
+            S.level_tile_begin.resize(S.cls_level_begin[c + 1]);
+            const int t_begin = S.ntiles;
+            schedule_class_merged(plan, lv, mi, mb, inm, S.tile_desc, S.tile_oclass, S.ntiles, rows, delay);
+            S.level_tile_begin[S.cls_level_begin[c]] = t_begin;
+            S.level_tile_begin[S.cls_level_begin[c] + 1] = S.ntiles;
+            S.max_class_tiles = std::max(S.max_class_tiles, S.ntiles - t_begin);
+            continue;
         }
         int nlev = 0;
         for (int e = 0; e < ne; ++e) nlev = std::max(nlev, lv[e] + 1);

@@ -119,6 +119,19 @@ extern "C" int plan_check_run(const pbte_problem_t *p, double tol, int max_class
     }
     const MarchSchedule S = build_march_schedule(plan, nclass, level.data(), cin.data(), cbin.data());
     if (info) info[2] = nclass, info[3] = S.ntiles, info[4] = S.max_levels;
+    if (info)
+    {
+        // how close behind its last prerequisite a tile follows (tiles the marching pipeline may have to wait for)
+        int close8 = 0, close16 = 0;
+        for (int t = 0; t < S.ntiles; ++t)
+        {
+            const int32_t *hdr = S.tile_desc.data() + ((size_t)t * S.rows + 1 + F) * kTileElems;
+            if (hdr[3] >= 0 && hdr[2] - hdr[3] <= 8) ++close8;
+            if (hdr[3] >= 0 && hdr[2] - hdr[3] <= 16) ++close16;
+        }
+        info[5] = close8;
+        info[6] = close16;
+    }
     // descriptor headers: operator class, level, index in class, last prerequisite tile (strictly earlier, covers every neighbour)
     for (int c = 0; c < nclass; ++c)
     {

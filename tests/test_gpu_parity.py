@@ -497,3 +497,24 @@ def test_representatives_only_image_gives_identical_results(name, monkeypatch):
             assert rel(full[k], reps[k]) <= tol_of(name, P), k
     print(f"{name}: matrix image {full['stats'].image_bytes} -> {reps['stats'].image_bytes} bytes, create {full['stats'].create_ms:.2f} -> {reps['stats'].create_ms:.2f} ms")
     hc.close()
+
+
+@pytest.mark.parametrize("name", ["tet_p2", "c2_hex_p2_small", "quad_p4", "tri_p3_si"])
+@pytest.mark.parametrize("persist", ["0", "1"])
+def test_list_scheduled_tiles_on_the_gpu(name, persist, monkeypatch):
+    """The marching kernels on the list-scheduled tile order (tiles filled across wavefront levels; the library's choice where level
+    tiles are less than 85 % full, i.e. refined simplex meshes), forced here with a short eligibility delay on small cases."""
+    monkeypatch.setenv("PBTE_TILE_MERGE", "1")
+    monkeypatch.setenv("PBTE_TILE_DELAY", "2")
+    monkeypatch.setenv("PBTE_MARCH_PERSIST", persist)
+    monkeypatch.setenv("PBTE_MARCH_REGOP", "0")
+    hc = host_case(name, refine=1 if name == "tet_p2" else 0)
+    P = hc.problem
+    iters = 2
+    want = orc.solve(P, iters, 0.0, cache_lu=False, threads=8)
+    got = gpu_solve(P, iters, kernel=3)
+    assert got["stats"].kernel_used == 3 and got["stats"].max_levels >= 1
+    tol = tol_of(name, P)
+    for k in ("Tc", "Qc", "Tv", "Qv", "coeff"):
+        assert rel(got[k], want[k]) <= tol, (k, rel(got[k], want[k]))
+    hc.close()

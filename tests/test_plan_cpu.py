@@ -37,7 +37,7 @@ def run_plan(lib, P, iters, tol=1e-12, max_classes=512, want_coeff=False):
     rc = lib.plan_check_run(C.byref(st), C.c_double(tol), max_classes, iters, Tc.ctypes.data_as(dp), Qc.ctypes.data_as(dp),
                             coeff.ctypes.data_as(dp) if want_coeff else None, info.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(fill))
     return rc, dict(Tc=Tc, Qc=Qc, coeff=coeff, noclass=int(info[0]), naclass=int(info[1]), nclass=int(info[2]), ntiles=int(info[3]),
-                    max_levels=int(info[4]), fill=fill.value)
+                    max_levels=int(info[4]), close8=int(info[5]), close16=int(info[6]), fill=fill.value)
 
 
 def rel(a, b):
@@ -93,4 +93,25 @@ def test_class_specific_couplings_split_classes(plan_lib):
     assert rc == 0 and r["naclass"] == 1 and r["noclass"] > 1
     o = orc.solve(P, 3, 0.0, cache_lu=True, threads=2)
     assert rel(r["coeff"], o["coeff"]) < 1e-10
+    hc.close()
+
+
+@pytest.mark.parametrize("delay", ["0", "3", "8"])
+@pytest.mark.parametrize("name,refine", [("tet_p2", 1), ("c2_hex_p2_small", 0), ("c1_tri_p1", 1), ("quad_p2", 1)])
+def test_list_scheduled_tiles_reproduce_oracle(plan_lib, name, refine, delay, monkeypatch):
+    """Tiles filled across wavefront levels (list scheduling, shared_plan.hpp: schedule_class_merged) instead of level by level:
+    walked in tile order, every upwind neighbour must already be computed, so the sweep still reproduces the oracle; the tiles are
+    at least as full as those of the level schedule when no eligibility delay is asked for."""
+    hc = host_case(name, refine=refine)
+    P = hc.problem
+    monkeypatch.setenv("PBTE_TILE_MERGE", "0")
+    rc, by_level = run_plan(plan_lib, P, 0)
+    monkeypatch.setenv("PBTE_TILE_MERGE", "1")
+    monkeypatch.setenv("PBTE_TILE_DELAY", delay)
+    rc, r = run_plan(plan_lib, P, 2, want_coeff=True)
+    assert rc == 0
+    if delay == "0":
+        assert r["ntiles"] <= by_level["ntiles"]
+    o = orc.solve(P, 2, 0.0, cache_lu=False, threads=4)
+    assert rel(r["Tc"], o["Tc"]) < 1e-11 and rel(r["coeff"], o["coeff"]) < 1e-10
     hc.close()
