@@ -1019,9 +1019,10 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
         CK(cudaMemsetAsync(h->m_progress.p, 0, h->m_progress.count * sizeof(int32_t), h->stream));
         CK(cudaStreamSynchronize(h->stream));
     }
-    // tail pass: enough slot chunks that the streaming CTAs fill the machine several times over
+    // tail pass: as few slot chunks as give every SM a streaming CTA.  Measured on C2 (228 element blocks; profiles/r02_kernel_probes.txt,
+    // runs j and k): 1 chunk 49 us, 2: 57, 4: 57, 8: 63, 16: 80, 32: 127 us: every extra chunk writes and re-reads a partial moment vector
     {
-        int chunks = (12 * 148 + h->tail_blocks - 1) / std::max(1, h->tail_blocks);
+        int chunks = (sms + h->tail_blocks - 1) / std::max(1, h->tail_blocks);
         chunks = std::max(1, std::min(chunks, std::min(64, std::max(1, ns / 8))));
         if (const char *ev = std::getenv("PBTE_TAIL_CHUNKS")) chunks = std::max(1, std::min(std::atoi(ev), std::max(1, ns)));
         h->tail_chunks = chunks;

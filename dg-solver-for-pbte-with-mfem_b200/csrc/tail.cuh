@@ -60,8 +60,14 @@ __device__ __forceinline__ bool last_arrival(unsigned *ticket, unsigned expected
     return last;
 }
 
+#ifndef PBTE_TAIL_MINBLOCKS
+#define PBTE_TAIL_MINBLOCKS 1
+#endif
+#ifndef PBTE_TAIL_INFLIGHT
+#define PBTE_TAIL_INFLIGHT 8
+#endif
 template <bool STREAM>
-__global__ void __launch_bounds__(kTailThreads) iteration_tail_kernel(DevProblem P, DevTail Z)
+__global__ void __launch_bounds__(kTailThreads, PBTE_TAIL_MINBLOCKS) iteration_tail_kernel(DevProblem P, DevTail Z)
 {
     if (*P.stop) return;
     __shared__ double sp[kMaxDim + 1][kTailMaxVals];
@@ -104,13 +110,14 @@ __global__ void __launch_bounds__(kTailThreads) iteration_tail_kernel(DevProblem
             __syncthreads();
             if (!valid) continue;
             int s = sb;
-            for (; s + 8 <= se; s += 8)
+            constexpr int NF = PBTE_TAIL_INFLIGHT;  // 16-byte loads in flight per thread
+            for (; s + NF <= se; s += NF)
             {
-                double2 w[8];
+                double2 w[NF];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) w[k] = __ldcs(reinterpret_cast<const double2 *>(u + (size_t)(s + k) * sblock));
+                for (int k = 0; k < NF; ++k) w[k] = __ldcs(reinterpret_cast<const double2 *>(u + (size_t)(s + k) * sblock));
 #pragma unroll
-                for (int k = 0; k < 8; ++k) add(s_fac[s + k - sb], w[k]);
+                for (int k = 0; k < NF; ++k) add(s_fac[s + k - sb], w[k]);
             }
             for (; s < se; ++s) add(s_fac[s - sb], __ldcs(reinterpret_cast<const double2 *>(u + (size_t)s * sblock)));
         }
