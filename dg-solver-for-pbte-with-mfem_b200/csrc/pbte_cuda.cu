@@ -163,6 +163,7 @@ struct pbte_handle
     // communication: one all-reduce of [Tc | Qc] per iteration, issued by the library when a communicator is attached
     ncclComm_t comm = nullptr;
     int comm_rank = 0, comm_size = 1;
+    bool qc_pending = false;  // the heat-flux moments of the last iteration are not all-reduced yet (complete_moments)
 
     // graph replay: [0] sweep + partial moments (the caller or NCCL reduces), [1] sweep + fused finish (whole single-GPU iteration),
     // [2] sweep + NCCL all-reduce + finish (whole multi-GPU iteration of this rank)
@@ -620,6 +621,8 @@ DevTail make_tail(pbte_handle *h, int nparts, int per, bool finish)
     Z.nparts = nparts;
     Z.slots_per_chunk = per;
     Z.finish = finish ? 1 : 0;
+    Z.m_begin = 0;
+    Z.m_end = 1 + h->dim;
     Z.part = h->partial.p;
     Z.mom = (!finish && h->comm) ? h->mom_part.p : h->mom.p;
     Z.tickets = h->tickets.p;
@@ -633,13 +636,40 @@ DevTail make_tail(pbte_handle *h, int nparts, int per, bool finish)
     return Z;
 }
 
-// The finish step on its own (after the caller's or NCCL's all-reduce of the moment vector).
-int enqueue_finish(pbte_handle *h)
+// The finish step on its own (after the caller's or NCCL's all-reduce of the moment vector).  tc_only: a multi-GPU iteration
+// all-reduces and finishes the temperature moment alone (all the next sweep and the stop test need); the heat-flux moments of the
+// last iteration follow once, at the next synchronisation point (complete_moments).
+int enqueue_finish(pbte_handle *h, bool tc_only = false)
 {
     const DevProblem P = make_dev_problem(h);
-    iteration_tail_kernel<false><<<h->tail_blocks, kTailThreads, 0, h->stream>>>(P, make_tail(h, 0, 0, true));
+    DevTail Z = make_tail(h, 0, 0, true);
+    if (tc_only) Z.m_end = 1;
+    iteration_tail_kernel<false><<<h->tail_blocks, kTailThreads, 0, h->stream>>>(P, Z);
     ++h->launches;
     CK(cudaGetLastError());
+    if (tc_only) h->qc_pending = true;
+    return PBTE_OK;
+}
+
+// Heat-flux moments of the last executed iteration: their partial sums still sit in mom_part (iterations after a stop are no-ops).
+// reduce = false: the caller has issued the all-reduce already (several handles of one process: one NCCL group).
+int complete_moments(pbte_handle *h, bool reduce = true)
+{
+    if (!h->comm || !h->qc_pending) return PBTE_OK;
+    const size_t block = (size_t)h->ne * h->n;
+    if (reduce)
+    {
+        const ncclResult_t r = ncclAllReduce(h->mom_part.p + block, h->mom.p + block, (size_t)h->dim * block, ncclDouble, ncclSum, h->comm, h->stream);
+        if (r != ncclSuccess) return fail(PBTE_ERR_CUDA, std::string("ncclAllReduce: ") + ncclGetErrorString(r));
+    }
+    const DevProblem P = make_dev_problem(h);
+    DevTail Z = make_tail(h, 0, 0, true);
+    Z.finish = 2;
+    Z.m_begin = 1;
+    iteration_tail_kernel<false><<<h->tail_blocks, kTailThreads, 0, h->stream>>>(P, Z);
+    ++h->launches;
+    CK(cudaGetLastError());
+    h->qc_pending = false;
     return PBTE_OK;
 }
 
@@ -1081,9 +1111,9 @@ int enqueue_iteration(pbte_handle *h)
     // one process per GPU: the rank's whole iteration (sweep, all-reduce, finish) replays as ONE graph; NCCL calls are capturable
     if (h->use_graph && h->nccl_in_graph) return graph_sweep(h, 2);
     if ((st = graph_sweep(h, 0))) return st;
-    const ncclResult_t r = ncclAllReduce(h->mom_part.p, h->mom.p, h->mom.count, ncclDouble, ncclSum, h->comm, h->stream);
+    const ncclResult_t r = ncclAllReduce(h->mom_part.p, h->mom.p, (size_t)h->ne * h->n, ncclDouble, ncclSum, h->comm, h->stream);
     if (r != ncclSuccess) return fail(PBTE_ERR_CUDA, std::string("ncclAllReduce: ") + ncclGetErrorString(r));
-    if ((st = enqueue_finish(h))) return st;
+    if ((st = enqueue_finish(h, true))) return st;
     CK(cudaEventRecord(h->ev2, h->stream));
     ++h->iter_enq;
     return PBTE_OK;
@@ -1710,6 +1740,8 @@ int pbte_cuda_download_moments(pbte_handle_t *h, double *Tc, double *Qc, double 
     int st = check_handle(h);
     if (st) return st;
     if (!h->mom.p) return fail(PBTE_ERR_STATE, "handle holds no moment state");
+    if (h->qc_pending && (Qc || Qv))
+        return fail(PBTE_ERR_STATE, "heat-flux moments of the enqueued iterations are not reduced yet: call pbte_cuda_iterate_sync (collective) first");
     DeviceGuard guard(h->device);
     const size_t block = (size_t)h->ne * h->n;
     if (Tc && Qc && Qc == Tc + block) CK(cudaMemcpyAsync(Tc, h->mom.p, (1 + h->dim) * block * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -1759,10 +1791,11 @@ int graph_sweep(pbte_handle *h, int mode)
     auto enqueue_all = [&]() -> int {
         int rc = enqueue_sweep(h, piv, mode == 1, &launches);
         if (rc || mode != 2) return rc;
-        const ncclResult_t r = ncclAllReduce(h->mom_part.p, h->mom.p, h->mom.count, ncclDouble, ncclSum, h->comm, h->stream);
+        // the temperature moment alone: the next sweep and the stop test need nothing else (complete_moments brings the rest)
+        const ncclResult_t r = ncclAllReduce(h->mom_part.p, h->mom.p, (size_t)h->ne * h->n, ncclDouble, ncclSum, h->comm, h->stream);
         if (r != ncclSuccess) return fail(PBTE_ERR_CUDA, std::string("ncclAllReduce: ") + ncclGetErrorString(r));
         ++launches;
-        if ((rc = enqueue_finish(h))) return rc;
+        if ((rc = enqueue_finish(h, true))) return rc;
         ++launches;
         return PBTE_OK;
     };
@@ -1820,6 +1853,7 @@ int graph_sweep(pbte_handle *h, int mode)
     h->launches += launches;
     ++h->sweeps;
     if (mode != 0) ++h->iter_enq;
+    if (mode == 2) h->qc_pending = true;
     if (piv == 1) h->pivots_recorded = true;
     return PBTE_OK;
 }
@@ -1863,7 +1897,7 @@ int solve_handles(pbte_handle **hs, int nh, int32_t max_iter, double tol, int32_
                 ncclGroupStart();
                 ncclResult_t r = ncclSuccess;
                 for (int i = 0; i < nh && r == ncclSuccess; ++i)
-                    r = ncclAllReduce(hs[i]->mom_part.p, hs[i]->mom.p, hs[i]->mom.count, ncclDouble, ncclSum, hs[i]->comm, hs[i]->stream);
+                    r = ncclAllReduce(hs[i]->mom_part.p, hs[i]->mom.p, (size_t)hs[i]->ne * hs[i]->n, ncclDouble, ncclSum, hs[i]->comm, hs[i]->stream);
                 const ncclResult_t r2 = ncclGroupEnd();
                 if (r != ncclSuccess || r2 != ncclSuccess)
                 {
@@ -1873,7 +1907,7 @@ int solve_handles(pbte_handle **hs, int nh, int32_t max_iter, double tol, int32_
                 for (int i = 0; i < nh && st == PBTE_OK; ++i)
                 {
                     DeviceGuard guard(hs[i]->device);
-                    if ((st = enqueue_finish(hs[i]))) break;
+                    if ((st = enqueue_finish(hs[i], true))) break;
                     if (cudaEventRecord(hs[i]->ev2, hs[i]->stream) != cudaSuccess) st = fail(PBTE_ERR_CUDA, "cudaEventRecord failed");
                     ++hs[i]->iter_enq;
                 }
@@ -1911,6 +1945,31 @@ int solve_handles(pbte_handle **hs, int nh, int32_t max_iter, double tol, int32_
         hs[i]->last_tv_norm = hs[0]->last_tv_norm;
         hs[i]->last_tc_norm = hs[0]->last_tc_norm;
         const int st2 = reset_ctrl(hs[i], 0.0);
+        if (st == PBTE_OK) st = st2;
+        cudaStreamSynchronize(hs[i]->stream);
+    }
+    // heat-flux moments of the last executed iteration (multi-GPU: all-reduced once, here)
+    if (nh > 1)
+    {
+        bool any = false;
+        for (int i = 0; i < nh; ++i) any = any || hs[i]->qc_pending;
+        if (any)
+        {
+            ncclGroupStart();
+            ncclResult_t r = ncclSuccess;
+            for (int i = 0; i < nh && r == ncclSuccess; ++i)
+            {
+                const size_t block = (size_t)hs[i]->ne * hs[i]->n;
+                r = ncclAllReduce(hs[i]->mom_part.p + block, hs[i]->mom.p + block, (size_t)hs[i]->dim * block, ncclDouble, ncclSum, hs[i]->comm, hs[i]->stream);
+            }
+            const ncclResult_t r2 = ncclGroupEnd();
+            if ((r != ncclSuccess || r2 != ncclSuccess) && st == PBTE_OK) st = fail(PBTE_ERR_CUDA, std::string("ncclAllReduce: ") + ncclGetErrorString(r != ncclSuccess ? r : r2));
+        }
+    }
+    for (int i = 0; i < nh; ++i)
+    {
+        DeviceGuard guard(hs[i]->device);
+        const int st2 = complete_moments(hs[i], nh == 1);
         if (st == PBTE_OK) st = st2;
         cudaStreamSynchronize(hs[i]->stream);
     }
@@ -1955,6 +2014,7 @@ int pbte_cuda_finish_iteration(pbte_handle_t *h, double *residual)
     }
     // cell integrals, norms of the stop test and the hand-over Tv_prev <- Tv, Tc_prev <- Tc (src/PBTESolver.cpp:313-329): one launch
     if ((st = enqueue_finish(h))) return st;
+    h->qc_pending = false;
     CK(cudaEventRecord(h->ev2, h->stream));
     const int64_t index = h->iter_enq++;
     st = read_history(h, index, nullptr, residual);
@@ -1977,6 +2037,7 @@ int pbte_cuda_iterate_sync(pbte_handle_t *h, int64_t *iterations, double *residu
     int st = check_handle(h);
     if (st) return st;
     DeviceGuard guard(h->device);
+    if ((st = complete_moments(h))) return st;  // collective when a communicator is attached
     CK(cudaStreamSynchronize(h->stream));
     read_timers(h);
     if (iterations) *iterations = h->iter_enq;

@@ -31,7 +31,8 @@ struct DevTail
 {
     int nparts;            // STREAM: slot chunks (gridDim.y); else partial vectors to add (0: `mom` already holds the sums)
     int slots_per_chunk;   // STREAM only
-    int finish;            // 1: go on to cell integrals / norms / hand-over
+    int finish;            // 1: go on to cell integrals / norms / hand-over; 2: cell integrals of the moments [m_begin, m_end) only
+    int m_begin, m_end;    // moments the finish part works on (a multi-GPU iteration all-reduces and finishes Tc alone, Qc once at the end)
     double *part;          // [nparts][1+dim][ne*n] partial sums (unused when nparts <= 1 && STREAM, or nparts == 0)
     double *mom;           // [1+dim][ne*n] result of the reduction (the vector a multi-GPU iteration all-reduces)
     unsigned *tickets;     // [gridDim.x + 1] arrival counters (zero between launches)
@@ -147,6 +148,7 @@ __global__ void __launch_bounds__(kTailThreads, PBTE_TAIL_MINBLOCKS) iteration_t
             for (int m = 0; m <= kMaxDim; ++m)
             {
                 if (m >= nm) break;
+                if (nparts == 0 && (m < Z.m_begin || m >= Z.m_end)) continue;
                 double a = 0.0, b = 0.0;
                 if (nparts == 0)
                 {
@@ -175,6 +177,7 @@ __global__ void __launch_bounds__(kTailThreads, PBTE_TAIL_MINBLOCKS) iteration_t
     if (!Z.finish) return;
 
     // ---- finish: cell integrals, norms, hand-over ----------------------------------------------------------------------------
+    const int mb = Z.m_begin, me = min(Z.m_end, nm);
     double c2 = 0.0;
     if (valid)
     {
@@ -182,26 +185,30 @@ __global__ void __launch_bounds__(kTailThreads, PBTE_TAIL_MINBLOCKS) iteration_t
 #pragma unroll
         for (int m = 0; m <= kMaxDim; ++m)
         {
-            if (m >= nm) break;
+            if (m >= me) break;
+            if (m < mb) continue;
             sp[m][le * n + i0] = v[m][0] * b0;
             if (has1) sp[m][le * n + i0 + 1] = v[m][1] * b1;
         }
-        // tc_prev rows are padded to np doubles; the padding stays zero
-        *reinterpret_cast<double2 *>(Z.tc_prev + (size_t)e * np + i0) = make_double2(v[0][0], has1 ? v[0][1] : 0.0);
-        c2 = v[0][0] * v[0][0] + (has1 ? v[0][1] * v[0][1] : 0.0);
+        if (mb == 0 && Z.finish == 1)
+        {
+            // tc_prev rows are padded to np doubles; the padding stays zero
+            *reinterpret_cast<double2 *>(Z.tc_prev + (size_t)e * np + i0) = make_double2(v[0][0], has1 ? v[0][1] : 0.0);
+            c2 = v[0][0] * v[0][0] + (has1 ? v[0][1] * v[0][1] : 0.0);
+        }
     }
     __syncthreads();
     double d2 = 0.0, t2 = 0.0;
     {
         // thread (m, element): sum over the dofs in ascending order, as the reference's loop does
         const int nel = min(epb, ne - (int)blockIdx.x * epb);
-        for (int idx = t; idx < nm * nel; idx += kTailThreads)
+        for (int idx = t; idx < (me - mb) * nel; idx += kTailThreads)
         {
-            const int m = idx / nel, l = idx - m * nel, ee = blockIdx.x * epb + l;
+            const int m = mb + idx / nel, l = idx - (m - mb) * nel, ee = blockIdx.x * epb + l;
             double s = 0.0;
             for (int i = 0; i < n; ++i) s += sp[m][l * n + i];
             Z.cell[(size_t)m * ne + ee] = s;
-            if (m == 0)
+            if (m == 0 && Z.finish == 1)
             {
                 const double d = s - Z.tv_prev[ee];
                 d2 += d * d;
@@ -210,6 +217,7 @@ __global__ void __launch_bounds__(kTailThreads, PBTE_TAIL_MINBLOCKS) iteration_t
             }
         }
     }
+    if (Z.finish == 2) return;
     // CTA partial sums in a fixed order: warp shuffle tree, then the warps in ascending order
     for (int off = 16; off > 0; off >>= 1)
     {
