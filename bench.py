@@ -53,6 +53,8 @@ EXTRA_WORKLOADS = {
                label="C3: builtin unit-cube-tet refine 3 (196608 tets), DG order 2 (ndof 10), 8 x 16 = 128 directions, non-gray Si = 40 bands"),
     "c5": dict(mesh="unit-square-quad", order=4, refine=5, angle_dim=2, polar=1, azimuth=64, num_spectral=20, bcs={1: -0.5, 2: -0.5, 3: 0.5, 4: -0.5},
                label="C5: builtin unit-square-quad refine 5 (65536 quads), DG order 4 (ndof 25), 64 azimuth directions (2-D), non-gray Si = 40 bands"),
+    "c4full": dict(mesh="unit-cube-hex", order=3, refine=3, angle_dim=3, polar=16, azimuth=32, num_spectral=20,
+                   label="C4 at full size: unit-cube-hex refine 3 = the 8-hex mesh file refined 4 times (32768 hexes), DG order 3 (ndof 64), 16 x 32 = 512 directions, 40 bands (4.29e10 updates per iteration, 344 GB of flux: 4 or 8 GPUs)"),
     "c4": dict(mesh="unit-cube-hex", order=3, refine=2, angle_dim=3, polar=16, azimuth=32, num_spectral=20,
                label="C4 (1-GPU strong-scaling point of SURVEY 8d): unit-cube-hex refine 2 (4096 hexes), DG order 3 (ndof 64), 16 x 32 = 512 directions, 40 bands"),
 }
@@ -405,6 +407,9 @@ def run_gpu(args, rank, world, local_rank):
     host_setup_s = time.perf_counter() - t_setup
     P = hc.problem
     k0, k1 = pb.partition_directions(P.ndir, world, rank)
+    if args.slice_of > 1:
+        # one GPU's share of an N-GPU strong-scaling run, measured alone (no all-reduce): the per-GPU sweep time of that point
+        k0, k1 = pb.partition_directions(P.ndir, args.slice_of, 0)
     stream = torch.cuda.Stream(device=local_rank)
     t_setup = time.perf_counter()
     solver = pb.Solver(P, device=local_rank, dir_range=(k0, k1), cache_policy=0, kernel=args.kernel, stream=stream.cuda_stream)
@@ -417,6 +422,8 @@ def run_gpu(args, rank, world, local_rank):
         sampler.launch()
     total_ms, res, clocks, launches = timed_iterations(solver, plumb, stream, args.steps, max(args.warmup, 3), sampler)
     U = P.updates_per_sweep  # all ranks together
+    if args.slice_of > 1:
+        U = P.ndof * P.ne * (k1 - k0) * P.nband  # the slice alone
     value = U * args.steps / (total_ms * 1e-3)
     sweep_ms, march_ms = sampled_kernel_times(solver, stream, torch)
     st1 = solver.stats()
@@ -558,7 +565,8 @@ def run_gpu(args, rank, world, local_rank):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": (f"{wl['label']} ({k1 - k0} directions on this GPU), reference-compatible local matrices; {U} updates per step" if strong else WORKLOAD_NAME),
+        "config": {"workload": (f"{wl['label']} ({k1 - k0} directions on this GPU), reference-compatible local matrices; {U} updates per step" if strong else WORKLOAD_NAME)
+                               + (f"; SLICE: one GPU's share of a {args.slice_of}-GPU run measured alone (value = this GPU's updates/s, no all-reduce)" if args.slice_of > 1 else ""),
                    "detail": f"{P.ne} elements, ndof {P.ndof}, {P.ndir} directions in all ({k1 - k0} per GPU), {P.nband} bands, reference-compatible local matrices; {U} updates per step",
                    "parallelism": (f"directions partitioned over {world} GPU(s), one FP64 all-reduce of the temperature moment Tc per step issued by the library (NCCL, inside the iteration's CUDA graph); the heat-flux moments Qc are all-reduced once, when the state is read out" if world > 1 else "single GPU"),
                    "l2_flush": f"none needed: the flux ({flux_mb:.0f} MB per GPU) is read and rewritten every step and exceeds the 126 MB L2",
@@ -606,6 +614,7 @@ def main():
     ap.add_argument("--no-general", action="store_true", help="skip the side measurement of the per-element LU kernel")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling record (full-size C3, directions split over the GPUs)")
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 warp-register, 3 shared-operator marching")
+    ap.add_argument("--slice-of", type=int, default=1, help="with --workload: run one GPU's direction share of an N-GPU strong-scaling run alone")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
