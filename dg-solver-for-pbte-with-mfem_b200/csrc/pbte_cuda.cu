@@ -14,6 +14,7 @@
 #include "tail.cuh"
 
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>  // header-only: ranges around the library's phases for nsys / ncu timelines (tracing)
 
 #include <algorithm>
 #include <array>
@@ -30,6 +31,12 @@ using namespace pbte_dev;
 
 namespace
 {
+struct NvtxRange
+{
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 thread_local std::string g_err = "no error";
 
 int fail(int status, const std::string &msg)
@@ -546,6 +553,7 @@ __global__ void __launch_bounds__(256) repack_blocks_kernel(int nblocks, int ne,
 
 int transfer_all_blocks(pbte_handle *h, double *host, bool upload)
 {
+    NvtxRange nvtx(upload ? "pbte_cuda_upload_coeff_all" : "pbte_cuda_download_coeff_all");
     const int nblk = h->nslots();
     if (nblk == 0) return PBTE_OK;
     const size_t block = (size_t)h->ne * h->n;
@@ -812,6 +820,15 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
     const pbte_host::MarchSchedule sched = pbte_host::build_march_schedule(plan, nclass, h->h_level.data(), cin.data(), cbin.data());
     h->march_ntiles = sched.ntiles;
     h->march_fill = sched.fill;
+    if (sched.mask_mismatch > 0)
+    {
+        // a direction (almost) tangential to a face: n.Omega changes sign inside an operator class; the shared operators would drop or
+        // invent an inflow term for those elements.  The per-element kernels take the mesh as it is.
+        if (h->kernel_choice == 3 || h->reps_only)
+            return fail(PBTE_ERR_INVALID, "shared-operator kernel declined: " + std::to_string(sched.mask_mismatch) +
+                                              " (direction, element) pairs see other inflow faces than their operator class (a direction tangential to a face within the class tolerance); use kernel 0 / 2 with PBTE_IMAGE=full or a smaller class_tol");
+        return PBTE_OK;
+    }
     if (h->kernel_choice == 0 && sched.fill < 0.4) return PBTE_OK;
 
     // operator block layout per slot: for every operator class P, then Q_j of the class's inflow faces (ascending j)
@@ -955,7 +972,7 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
     {
         // operator storage: split order where a persistent CTA stages its slot's block, fragment pairs where a classic CTA stages it or
         // the consumers keep it in registers, compact row-major where every tile reads its operators from global memory
-        h->march_op_layout = h->march_regop ? 0 : (h->march_stage ? (h->march_persist ? 2 : 0) : 1);
+        h->march_op_layout = h->march_regop ? 0 : (h->march_stage ? (h->march_persist ? 2 : 0) : (PBTE_COMPACT_OPS == 0 && !h->march_persist ? 0 : 1));
         h->march_op_stride = h->march_op_layout == 0 ? (int)FR : (h->march_op_layout == 2 ? (int)SP : compact_doubles(n));
         std::vector<unsigned long long> slot_base(ns);
         size_t total = 0;
@@ -1184,6 +1201,7 @@ void pbte_cuda_default_options(pbte_options_t *opt)
 int pbte_cuda_create(const pbte_problem_t *p, const pbte_options_t *opt_in, pbte_handle_t **out)
 {
     if (!p || !out) return fail(PBTE_ERR_INVALID, "null argument");
+    NvtxRange nvtx("pbte_cuda_create");
     *out = nullptr;
     if (p->abi_version != PBTE_ABI_VERSION) return fail(PBTE_ERR_INVALID, "problem image has a different ABI version");
     if (p->ne < 0 || p->ndof < 0 || p->ndir < 0 || p->nband < 0 || p->dim < 0 || p->dim > 3 || p->nfaces < 0 || p->nfaces > PBTE_MAX_FACES)
@@ -1355,6 +1373,7 @@ int pbte_cuda_build_schedule(pbte_handle_t *h)
     int st = check_handle(h);
     if (st) return st;
     if (!h->has_topology || !h->has_dirs) return fail(PBTE_ERR_STATE, "build_schedule needs face_nbr, face_normal and directions");
+    NvtxRange nvtx("pbte_cuda_build_schedule");
     DeviceGuard guard(h->device);
     const int ne = h->ne, F = h->F, nloc = h->nloc();
     h->scheduled = false;
@@ -1865,6 +1884,7 @@ int graph_sweep(pbte_handle *h, int mode)
 int solve_handles(pbte_handle **hs, int nh, int32_t max_iter, double tol, int32_t *iters_done, double *residual, double *history,
                   pbte_iteration_callback_t cb, void *user)
 {
+    NvtxRange nvtx("pbte_cuda_solve");
     int st = PBTE_OK;
     for (int i = 0; i < nh; ++i)
     {

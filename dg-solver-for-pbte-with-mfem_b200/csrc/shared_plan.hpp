@@ -280,6 +280,9 @@ struct MarchSchedule
                                            // elements lies in a tile with an index <= that
     std::vector<uint8_t> cls_inmask;       // [nclass][noclass] canonical inflow faces (interior or wall) of the class representative
     double fill = 0.0;                     // elements / (8 * tiles)
+    int64_t mask_mismatch = 0;             // (DAG class, element) pairs whose own inflow faces differ from their operator class's: the
+                                           // normals of a class agree to the class tolerance only, so n.Omega may change sign inside
+                                           // a class for a direction (almost) tangential to a face; the marching path is declined then
 };
 
 // Tiles by list scheduling instead of level by level (build_march_schedule, default): a wavefront level of a DAG class rarely holds
@@ -466,6 +469,18 @@ inline MarchSchedule build_march_schedule_mode(const SharedPlan &plan, int nclas
             }
             inm[o] = (uint8_t)m;
             S.max_inflow = std::max(S.max_inflow, (int)__builtin_popcount(m));
+        }
+        // every element must see exactly the inflow faces its operator class was built for (its operators Q_f, h_f exist for those)
+        for (int e = 0; e < ne; ++e)
+        {
+            unsigned m = 0;
+            for (int j = 0; j < F; ++j)
+            {
+                const size_t cs = (size_t)e * F + j;
+                if (plan.cnbr[cs] == PBTE_FACE_NONE) continue;
+                if (((mi[e] | mb[e]) >> plan.cface[cs]) & 1u) m |= 1u << j;
+            }
+            if (m != inm[plan.elem_oclass[e]]) ++S.mask_mismatch;
         }
         if (merge)
         {

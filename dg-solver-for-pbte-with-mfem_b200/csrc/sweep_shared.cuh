@@ -1044,7 +1044,11 @@ __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_
     constexpr bool kPairTiles = false;
     using G = Frag<N>;
     constexpr int MT = G::MT, MP = G::MP, KS = G::KS, FR = G::FR;
-    constexpr int OPS = STAGE ? FR : compact_doubles(N);  // doubles per operator: staged operators are in fragment order, others compact
+#ifndef PBTE_COMPACT_OPS
+#define PBTE_COMPACT_OPS 1  // 0 (experiment): unstaged operators in fragment-pair order as well (192 instead of 100 doubles for ndof 10, one 16-byte load per k step)
+#endif
+    constexpr bool FRAG_B = STAGE || PBTE_COMPACT_OPS == 0;
+    constexpr int OPS = FRAG_B ? FR : compact_doubles(N);  // doubles per operator: staged operators are in fragment order, others compact
     constexpr int NP = (N + 1) & ~1;        // global row stride (doubles): 16-byte aligned rows
     constexpr int NS = stage_stride(N);     // shared-memory row stride
     constexpr int CH = NP / 2;              // 16-byte chunks per row
@@ -1310,7 +1314,7 @@ __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_
 #pragma unroll
                             for (int Ip = 0; Ip < MP; ++Ip)
                             {
-                                if constexpr (STAGE) bq[k][Ip] = bp[(Ip * KS + k0 + k) * 32];
+                                if constexpr (FRAG_B) bq[k][Ip] = bp[(Ip * KS + k0 + k) * 32];
                                 else
                                 {
                                     // compact row-major operator: this lane's B entries of row blocks 2Ip and 2Ip+1 are R[row][col]

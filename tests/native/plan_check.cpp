@@ -131,6 +131,7 @@ extern "C" int plan_check_run(const pbte_problem_t *p, double tol, int max_class
         }
         info[5] = close8;
         info[6] = close16;
+        info[7] = (int32_t)std::min<int64_t>(S.mask_mismatch, INT32_MAX);
     }
     // descriptor headers: operator class, level, index in class, last prerequisite tile (strictly earlier, covers every neighbour)
     for (int c = 0; c < nclass; ++c)

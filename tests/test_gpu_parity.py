@@ -518,3 +518,29 @@ def test_list_scheduled_tiles_on_the_gpu(name, persist, monkeypatch):
     for k in ("Tc", "Qc", "Tv", "Qv", "coeff"):
         assert rel(got[k], want[k]) <= tol, (k, rel(got[k], want[k]))
     hc.close()
+
+
+def test_sign_flip_inside_an_operator_class_declines_the_marching_path(monkeypatch):
+    """an element whose normal equals its class representative's within the class tolerance, but whose n.Omega has the other
+    sign for a direction tangential to the face, must not be swept with the class's operators: the library counts such pairs when it
+    plans the tiles, the automatic choice falls back to the per-element kernel (same numbers as the oracle), kernel 3 is refused."""
+    monkeypatch.setenv("PBTE_IMAGE", "full")
+    hc = host_case("quad_p2")
+    P = hc.problem
+    P.dir[0] = (0.0, 1.0, 0.0)
+    e = P.ne // 2
+    for f in range(P.nfaces):
+        if abs(P.face_normal[e, f, 0]) == 1.0:
+            P.face_normal[e, f, 1] = -1e-14 * P.face_normal[e, f, 0]
+    want = orc.solve(P, 2, 0.0, cache_lu=False, threads=4)
+    got = gpu_solve(P, 2, kernel=0)
+    assert got["stats"].kernel_used == 2
+    assert np.array_equal(got["orders"], orc.sweep_orders(P))
+    for k in ("Tc", "Qc", "coeff"):
+        assert rel(got[k], want[k]) <= 1e-10, (k, rel(got[k], want[k]))
+    s = pb.Solver(P, kernel=3)
+    with pytest.raises(pb.PbteError) as ei:
+        s.build_schedule()
+    assert ei.value.status == -1
+    s.close()
+    hc.close()

@@ -37,7 +37,7 @@ def run_plan(lib, P, iters, tol=1e-12, max_classes=512, want_coeff=False):
     rc = lib.plan_check_run(C.byref(st), C.c_double(tol), max_classes, iters, Tc.ctypes.data_as(dp), Qc.ctypes.data_as(dp),
                             coeff.ctypes.data_as(dp) if want_coeff else None, info.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(fill))
     return rc, dict(Tc=Tc, Qc=Qc, coeff=coeff, noclass=int(info[0]), naclass=int(info[1]), nclass=int(info[2]), ntiles=int(info[3]),
-                    max_levels=int(info[4]), close8=int(info[5]), close16=int(info[6]), fill=fill.value)
+                    max_levels=int(info[4]), close8=int(info[5]), close16=int(info[6]), mask_mismatch=int(info[7]), fill=fill.value)
 
 
 def rel(a, b):
@@ -114,4 +114,26 @@ def test_list_scheduled_tiles_reproduce_oracle(plan_lib, name, refine, delay, mo
         assert r["ntiles"] <= by_level["ntiles"]
     o = orc.solve(P, 2, 0.0, cache_lu=False, threads=4)
     assert rel(r["Tc"], o["Tc"]) < 1e-11 and rel(r["coeff"], o["coeff"]) < 1e-10
+    hc.close()
+
+
+def test_axis_aligned_direction_and_sign_flip_inside_a_class(plan_lib):
+    """A direction exactly tangential to faces of a Cartesian mesh is consistent (n.Omega == 0 for every element of the class); an
+    element whose normal differs from its class representative's by less than the class tolerance but flips the sign of n.Omega is
+    counted, so that the library declines the shared-operator path instead of dropping that element's inflow term."""
+    hc = host_case("quad_p2")
+    P = hc.problem
+    P.dir[0] = (0.0, 1.0, 0.0)   # tangential to the x-faces
+    P.dir[1] = (1.0, 0.0, 0.0)
+    rc, r = run_plan(plan_lib, P, 2, want_coeff=True)
+    assert rc == 0 and r["mask_mismatch"] == 0
+    o = orc.solve(P, 2, 0.0, cache_lu=False, threads=2)
+    assert rel(r["coeff"], o["coeff"]) < 1e-10
+    # one element's x-normals tilt by 1e-14: same operator class (tolerance 1e-12), but for direction 0 its n.Omega is -1e-14 / +1e-14
+    e = P.ne // 2
+    for f in range(P.nfaces):
+        if abs(P.face_normal[e, f, 0]) == 1.0:
+            P.face_normal[e, f, 1] = -1e-14 * P.face_normal[e, f, 0]
+    rc, r = run_plan(plan_lib, P, 0)
+    assert r["noclass"] == 1 and r["mask_mismatch"] > 0
     hc.close()
