@@ -120,6 +120,7 @@ struct pbte_handle
     int max_classes = 512;
     pbte_host::SharedPlan plan;
     int march_ntiles = 0;
+    int64_t march_mask_mismatch = 0;
     double march_fill = 0.0;
     bool march_stage = false;
     DevBuf<long long> m_trace;  // development builds only
@@ -820,13 +821,16 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
     const pbte_host::MarchSchedule sched = pbte_host::build_march_schedule(plan, nclass, h->h_level.data(), cin.data(), cbin.data());
     h->march_ntiles = sched.ntiles;
     h->march_fill = sched.fill;
-    if (sched.mask_mismatch > 0)
+    h->march_mask_mismatch = sched.mask_mismatch;
+    if (sched.mask_mismatch > 0 && h->class_tol > 1e-11)
     {
-        // a direction (almost) tangential to a face: n.Omega changes sign inside an operator class; the shared operators would drop or
-        // invent an inflow term for those elements.  The per-element kernels take the mesh as it is.
+        // A direction (almost) tangential to a face: n.Omega changes sign inside an operator class, whose normals agree to class_tol
+        // only; the shared operators then drop or invent an inflow term of relative size <= class_tol for those elements.  At the
+        // default tolerance (1e-12) that is below the parity bar and the path runs (the count is reported: pbte_stats_t::
+        // march_mask_mismatch); with a looser tolerance the per-element kernels take the mesh as it is.
         if (h->kernel_choice == 3 || h->reps_only)
             return fail(PBTE_ERR_INVALID, "shared-operator kernel declined: " + std::to_string(sched.mask_mismatch) +
-                                              " (direction, element) pairs see other inflow faces than their operator class (a direction tangential to a face within the class tolerance); use kernel 0 / 2 with PBTE_IMAGE=full or a smaller class_tol");
+                                              " (direction, element) pairs see other inflow faces than their operator class (a direction tangential to a face within class_tol > 1e-11); use kernel 0 / 2 with PBTE_IMAGE=full or a smaller class_tol");
         return PBTE_OK;
     }
     if (h->kernel_choice == 0 && sched.fill < 0.4) return PBTE_OK;
@@ -2277,6 +2281,7 @@ int pbte_cuda_get_stats(pbte_handle_t *h, pbte_stats_t *s)
     s->image_bytes = h->image_bytes;
     s->create_ms = h->create_ms;
     s->image_reps_only = h->reps_only ? 1 : 0;
+    s->march_mask_mismatch = (int32_t)std::min<int64_t>(h->march_mask_mismatch, INT32_MAX);
     s->march_persistent = h->kernel_used == 3 && h->march_persist ? 1 : 0;
     s->march_ctas = h->kernel_used == 3 ? (h->march_persist ? h->march_ncta : h->nslots()) : 0;
     return PBTE_OK;

@@ -101,7 +101,9 @@ __global__ void __launch_bounds__(regop_threads(N), regop_ctas(N)) sweep_march_r
     const size_t h_one = (size_t)F * N;
     const size_t h_doubles = S.h_smem ? h_one : 0;
     unsigned char *ring = reinterpret_cast<unsigned char *>(s_h + h_doubles);
-    ring = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(ring) + 15) & ~(uintptr_t)15);
+    // 16-byte alignment as an OFFSET from the shared-memory base (an integer round trip of the pointer would make every ring access a
+    // generic load instead of LDS)
+    ring = sm_raw + ((static_cast<size_t>(ring - sm_raw) + 15) & ~static_cast<size_t>(15));
     for (size_t i = threadIdx.x; i < h_doubles; i += blockDim.x) s_h[i] = S.oph[(size_t)s * h_one + i];
     for (int i = threadIdx.x; i < 64; i += blockDim.x) prog[i] = 0;
     // the ring starts zeroed: copies write NP doubles per row, the k padding up to NS stays zero for the whole kernel

@@ -546,7 +546,9 @@ __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_
     double *s_h = reinterpret_cast<double *>(empty + R);  // [noclass][F][N] wall vectors of the piece's slot (when S.h_smem)
     const size_t h_doubles = S.h_smem ? (size_t)noc * F * N : 0;
     unsigned char *ring = reinterpret_cast<unsigned char *>(s_h + h_doubles);
-    ring = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(ring) + 15) & ~(uintptr_t)15);
+    // 16-byte alignment as an OFFSET from the shared-memory base (an integer round trip of the pointer would make every ring access a
+    // generic load instead of LDS)
+    ring = sm_raw + ((static_cast<size_t>(ring - sm_raw) + 15) & ~static_cast<size_t>(15));
 
     // the ring starts zeroed: copies write NP doubles per row, the k padding up to NS stays zero for the whole kernel
     for (size_t i = threadIdx.x; i < (size_t)R * slot_bytes / 16; i += blockDim.x) reinterpret_cast<uint4 *>(ring)[i] = make_uint4(0, 0, 0, 0);
@@ -1079,7 +1081,9 @@ __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_
     double *s_h = reinterpret_cast<double *>(empty + R);  // [noclass][F][N] wall vectors of this slot (when S.h_smem)
     const size_t h_doubles = S.h_smem ? (size_t)noc * F * N : 0;
     unsigned char *ring = reinterpret_cast<unsigned char *>(s_h + h_doubles);
-    ring = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(ring) + 15) & ~(uintptr_t)15);
+    // 16-byte alignment as an OFFSET from the shared-memory base (an integer round trip of the pointer would make every ring access a
+    // generic load instead of LDS)
+    ring = sm_raw + ((static_cast<size_t>(ring - sm_raw) + 15) & ~static_cast<size_t>(15));
     for (size_t i = threadIdx.x; i < h_doubles; i += blockDim.x) s_h[i] = S.oph[(size_t)s * noc * F * N + i];
 
     for (int i = threadIdx.x; i <= nlev; i += blockDim.x) ltb[i] = S.level_tile_begin[lb + i];

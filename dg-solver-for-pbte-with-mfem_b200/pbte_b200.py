@@ -53,7 +53,7 @@ class Stats(C.Structure):
                 ("n_operator_classes", C.c_int32), ("march_tiles", C.c_int32), ("march_variant", C.c_int32),
                 ("march_fill", C.c_double), ("operator_bytes", C.c_int64), ("last_march_ms", C.c_double),
                 ("march_persistent", C.c_int32), ("march_ctas", C.c_int32), ("image_bytes", C.c_int64), ("create_ms", C.c_double),
-                ("image_reps_only", C.c_int32), ("reserved0", C.c_int32)]
+                ("image_reps_only", C.c_int32), ("march_mask_mismatch", C.c_int32)]
 
 
 class HostSpec(C.Structure):
@@ -348,7 +348,7 @@ class HostSolver:
 class Solver:
     """One device handle of the C ABI (pbte_cuda_create .. pbte_cuda_destroy)."""
 
-    def __init__(self, problem, device=-1, dir_range=None, cache_policy=0, kernel=0, use_graph=1, stream=None):
+    def __init__(self, problem, device=-1, dir_range=None, cache_policy=0, kernel=0, use_graph=1, stream=None, class_tol=None):
         self.lib = cuda_lib()
         self.problem = problem
         self._struct = problem.struct()
@@ -359,6 +359,8 @@ class Solver:
             opt.dir_begin, opt.dir_end = dir_range
         if stream is not None:
             opt.stream = stream
+        if class_tol is not None:
+            opt.class_tol = class_tol
         self.dir_range = dir_range if dir_range is not None else (0, problem.ndir)
         self._h = C.c_void_p()
         _ck(self.lib.pbte_cuda_create(C.byref(self._struct), C.byref(opt), C.byref(self._h)))

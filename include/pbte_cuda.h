@@ -237,7 +237,8 @@ typedef struct pbte_stats
     int64_t image_bytes;      /* device bytes of local matrices held: the per-element image and/or the class representatives */
     double create_ms;         /* host time of pbte_cuda_create (classification + uploads) */
     int32_t image_reps_only;  /* 1 = only the operator-class representatives' matrices were uploaded (marching path only) */
-    int32_t reserved0;
+    int32_t march_mask_mismatch; /* (upwind DAG, element) pairs whose n.Omega sign differs from their operator class's for a direction
+                                    tangential to a face within class_tol: their inflow term of relative size <= class_tol is dropped */
 } pbte_stats_t;
 int pbte_cuda_get_stats(pbte_handle_t *h, pbte_stats_t *stats);
 /* The cudaStream_t the handle launches on (for CUDA-event timing by the caller). */

@@ -520,10 +520,11 @@ def test_list_scheduled_tiles_on_the_gpu(name, persist, monkeypatch):
     hc.close()
 
 
-def test_sign_flip_inside_an_operator_class_declines_the_marching_path(monkeypatch):
+def test_sign_flip_inside_an_operator_class(monkeypatch):
     """an element whose normal equals its class representative's within the class tolerance, but whose n.Omega has the other
-    sign for a direction tangential to the face, must not be swept with the class's operators: the library counts such pairs when it
-    plans the tiles, the automatic choice falls back to the per-element kernel (same numbers as the oracle), kernel 3 is refused."""
+    sign for a direction tangential to the face, is swept with its class's operators: an inflow term of relative size <= class_tol
+    is dropped for it.  The planner counts such (upwind DAG, element) pairs; at the default tolerance (1e-12) the marching path runs
+    and stays within the parity bar, with a tolerance above 1e-11 it is declined (automatic choice: per-element kernel; kernel 3: refused)."""
     monkeypatch.setenv("PBTE_IMAGE", "full")
     hc = host_case("quad_p2")
     P = hc.problem
@@ -533,12 +534,16 @@ def test_sign_flip_inside_an_operator_class_declines_the_marching_path(monkeypat
         if abs(P.face_normal[e, f, 0]) == 1.0:
             P.face_normal[e, f, 1] = -1e-14 * P.face_normal[e, f, 0]
     want = orc.solve(P, 2, 0.0, cache_lu=False, threads=4)
-    got = gpu_solve(P, 2, kernel=0)
-    assert got["stats"].kernel_used == 2
+    got = gpu_solve(P, 2, kernel=3)
+    assert got["stats"].kernel_used == 3 and got["stats"].march_mask_mismatch > 0
     assert np.array_equal(got["orders"], orc.sweep_orders(P))
     for k in ("Tc", "Qc", "coeff"):
         assert rel(got[k], want[k]) <= 1e-10, (k, rel(got[k], want[k]))
-    s = pb.Solver(P, kernel=3)
+    loose = gpu_solve(P, 2, kernel=0, class_tol=1e-9)
+    assert loose["stats"].kernel_used == 2
+    for k in ("Tc", "Qc", "coeff"):
+        assert rel(loose[k], want[k]) <= 1e-10, (k, rel(loose[k], want[k]))
+    s = pb.Solver(P, kernel=3, class_tol=1e-9)
     with pytest.raises(pb.PbteError) as ei:
         s.build_schedule()
     assert ei.value.status == -1
