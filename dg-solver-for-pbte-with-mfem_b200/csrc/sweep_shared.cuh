@@ -1021,6 +1021,9 @@ __device__ __forceinline__ void classic_bulk_stage(void *dst, const void *src, u
     }
 }
 
+// (Measured and dropped in round 2, profiles/r02_kernel_probes.txt run n: handing the ring slot back before the last matrix block of
+// a tile - all A fragments of that block loaded first, the hand-over guarded by a consumer of every load - costs more in exposed load
+// latency than the earlier refill returns: C2 0.392 against 0.369 ms, C3 slice 3.29 against 2.73 ms.)
 // One CTA per slot, one pass over the slot's tiles (the kernel of round 1): kept beside the persistent kernel because it is the faster of
 // the two wherever cutting slots into pieces buys nothing (no more slots than resident CTAs: C2) and for operators read from global
 // memory (tetrahedra): measured side by side in profiles/r02_kernel_probes.txt (C2 0.380 against 0.389 ms, C3 slice 3.59 against 3.89 ms;
@@ -1389,9 +1392,9 @@ __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_
 #pragma unroll
                     for (int I = 0; I < MT; ++I)
                     {
+                        // 16-byte stores; an odd ndof has one padding column per row, which stays zero
                         const int d0 = 8 * I + 2 * r;
-                        if (d0 < N) dst[d0] = acc[t][I][0];
-                        if (d0 + 1 < N) dst[d0 + 1] = acc[t][I][1];
+                        if (d0 < NP) *reinterpret_cast<double2 *>(dst + d0) = make_double2(acc[t][I][0], d0 + 1 < N ? acc[t][I][1] : 0.0);
                     }
                 }
             PBTE_STAMP(i0, 10);
