@@ -362,11 +362,31 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Wait for a barrier phase.  A failed try_wait comes back after a short, implementation-defined time; polling it in a tight loop
+// made waiting warps the main source of issued instructions (ncu source page of the C2 kernel: 29 M polls for 136 k tiles).
+// PBTE_WAIT_HINT_NS > 0 passes a suspend-time hint to try_wait, PBTE_WAIT_SLEEP_NS > 0 sleeps between polls.
+#ifndef PBTE_WAIT_HINT_NS
+#define PBTE_WAIT_HINT_NS 0
+#endif
+#ifndef PBTE_WAIT_SLEEP_NS
+#define PBTE_WAIT_SLEEP_NS 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     uint32_t ok = 0;
     while (!ok)
     {
+#if PBTE_WAIT_HINT_NS > 0
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)PBTE_WAIT_HINT_NS)
+            : "memory");
+#else
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
@@ -376,6 +396,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
             : "=r"(ok)
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
+#endif
+#if PBTE_WAIT_SLEEP_NS > 0
+        if (!ok) __nanosleep(PBTE_WAIT_SLEEP_NS);
+#endif
     }
 }
 // one non-blocking probe of a barrier phase

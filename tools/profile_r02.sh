@@ -15,6 +15,11 @@ ncu --set full --clock-control none --import-source on -k regex:"sweep_march" -s
 P3="python tools/kernel_probe.py ncu c3s"
 $P3 > /dev/null 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:"sweep_march" -s 6 -c 1 -o $O/r02_c3s_march_tets $P3 > $O/r02_prof_ncu_c3s.log 2>&1
+PK="python -c \"import sys; sys.path.insert(0, 'dg-solver-for-pbte-with-mfem_b200'); import pbte_b200 as pb; print(pb.measure_peaks(0))\""
+eval $PK > $O/r02_peaks_plain.log 2>&1 &&
+eval ncu --set full --clock-control none -k regex:"dmma_peak|dfma_peak|copy_kernel" -c 6 -o $O/r02_peak_probes $PK > $O/r02_prof_ncu_peaks.log 2>&1
+[ -f $O/r02_peak_probes.ncu-rep ] && ncu -i $O/r02_peak_probes.ncu-rep --page raw --csv > $O/r02_peak_probes_ncu_raw.csv 2>/dev/null
+rm -f $O/r02_peak_probes.ncu-rep
 # the raw pages travel back as CSV (gpurun merges at most 64 MiB); only the C2 report itself is kept
 for r in r02_c2_march_tail r02_c5s_march_persistent r02_c3s_march_tets; do
     [ -f $O/$r.ncu-rep ] && ncu -i $O/$r.ncu-rep --page raw --csv > $O/${r}_ncu_raw.csv 2>/dev/null
