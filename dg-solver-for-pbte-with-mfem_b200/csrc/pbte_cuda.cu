@@ -172,6 +172,13 @@ struct pbte_handle
     ncclComm_t comm = nullptr;
     int comm_rank = 0, comm_size = 1;
     bool qc_pending = false;  // the heat-flux moments of the last iteration are not all-reduced yet (complete_moments)
+    // exchange of the temperature partial sums over NVLink peer memory (csrc/tail.cuh): this rank's buffer, the peers' buffers as
+    // mapped into this process, the epoch counter
+    bool peer_mode = false;
+    DevBuf<double> xchg;
+    DevBuf<long long> xchg_epoch;
+    DevBuf<const double *> d_peers;
+    std::vector<void *> ipc_opened;  // peer mappings opened with cudaIpcOpenMemHandle (closed at detach)
 
     // graph replay: [0] sweep + partial moments (the caller or NCCL reduces), [1] sweep + fused finish (whole single-GPU iteration),
     // [2] sweep + NCCL all-reduce + finish (whole multi-GPU iteration of this rank)
@@ -199,6 +206,7 @@ struct pbte_handle
     ~pbte_handle()
     {
         drop_graphs();
+        for (void *q : ipc_opened) cudaIpcCloseMemHandle(q);
         if (comm) ncclCommDestroy(comm);
         for (cudaEvent_t e : ev_iter)
             if (e) cudaEventDestroy(e);
@@ -642,17 +650,24 @@ DevTail make_tail(pbte_handle *h, int nparts, int per, bool finish)
     Z.block_part = h->block_part.p;
     Z.ctrl = h->ctrl.p;
     Z.hist = h->d_hist;
+    Z.peer = 0;
+    Z.nranks = h->comm_size;
+    Z.rank = h->comm_rank;
+    Z.xchg = h->xchg.p;
+    Z.peers = h->d_peers.p;
+    Z.epoch = h->xchg_epoch.p;
     return Z;
 }
 
 // The finish step on its own (after the caller's or NCCL's all-reduce of the moment vector).  tc_only: a multi-GPU iteration
 // all-reduces and finishes the temperature moment alone (all the next sweep and the stop test need); the heat-flux moments of the
 // last iteration follow once, at the next synchronisation point (complete_moments).
-int enqueue_finish(pbte_handle *h, bool tc_only = false)
+int enqueue_finish(pbte_handle *h, bool tc_only = false, bool peer = false)
 {
     const DevProblem P = make_dev_problem(h);
     DevTail Z = make_tail(h, 0, 0, true);
     if (tc_only) Z.m_end = 1;
+    if (peer) Z.peer = 2;
     iteration_tail_kernel<false><<<h->tail_blocks, kTailThreads, 0, h->stream>>>(P, Z);
     ++h->launches;
     CK(cudaGetLastError());
@@ -684,7 +699,7 @@ int complete_moments(pbte_handle *h, bool reduce = true)
 
 // Enqueue the kernels of one sweep on the handle's stream.  piv: 0 search, 1 search+record, 2 replay.  fuse: the tail kernel goes
 // on to the finish step (single-GPU iteration: the whole iteration tail is one launch).
-int enqueue_sweep(pbte_handle *h, int piv, bool fuse, int64_t *launch_count)
+int enqueue_sweep(pbte_handle *h, int piv, bool fuse, int64_t *launch_count, bool peer = false)
 {
     const DevProblem P = make_dev_problem(h);
     int64_t launches = 0;
@@ -693,6 +708,16 @@ int enqueue_sweep(pbte_handle *h, int piv, bool fuse, int64_t *launch_count)
         // a rank without directions contributes zeros
         double *dst = (!fuse && h->comm) ? h->mom_part.p : h->mom.p;
         CK(cudaMemsetAsync(dst, 0, h->mom.count * sizeof(double), h->stream));
+        if (peer)
+        {
+            // ... and publishes them like every other rank (the zeroed partial vector is "summed" into the exchange buffer)
+            DevTail Z = make_tail(h, 1, 0, false);
+            Z.part = h->mom_part.p;
+            Z.peer = 1;
+            iteration_tail_kernel<false><<<h->tail_blocks, kTailThreads, 0, h->stream>>>(P, Z);
+            ++launches;
+            CK(cudaGetLastError());
+        }
         if (fuse)
         {
             iteration_tail_kernel<false><<<h->tail_blocks, kTailThreads, 0, h->stream>>>(P, make_tail(h, 0, 0, true));
@@ -750,7 +775,9 @@ int enqueue_sweep(pbte_handle *h, int piv, bool fuse, int64_t *launch_count)
         }
         // [Tc | Qc] by one streaming pass over the flux; its last CTAs finish the iteration when `fuse`
         const int chunks = h->tail_chunks, per = (h->nslots() + chunks - 1) / chunks;
-        iteration_tail_kernel<true><<<dim3((unsigned)h->tail_blocks, (unsigned)chunks), kTailThreads, 0, h->stream>>>(P, make_tail(h, chunks, per, fuse));
+        DevTail Z = make_tail(h, chunks, per, fuse);
+        if (peer) Z.peer = 1;
+        iteration_tail_kernel<true><<<dim3((unsigned)h->tail_blocks, (unsigned)chunks), kTailThreads, 0, h->stream>>>(P, Z);
         CK(cudaGetLastError());
         if (launch_count) *launch_count = 2;
         return PBTE_OK;
@@ -779,7 +806,11 @@ int enqueue_sweep(pbte_handle *h, int piv, bool fuse, int64_t *launch_count)
         }
     }
     // class partials -> moment vector (ascending class order), then the finish step when `fuse`
-    iteration_tail_kernel<false><<<h->tail_blocks, kTailThreads, 0, h->stream>>>(P, make_tail(h, h->nclass, 0, fuse));
+    {
+        DevTail Z = make_tail(h, h->nclass, 0, fuse);
+        if (peer) Z.peer = 1;
+        iteration_tail_kernel<false><<<h->tail_blocks, kTailThreads, 0, h->stream>>>(P, Z);
+    }
     ++launches;
     CK(cudaGetLastError());
     if (launch_count) *launch_count = launches;
@@ -1130,7 +1161,7 @@ int enqueue_iteration(pbte_handle *h)
     int st;
     if (!h->comm) return graph_sweep(h, 1);
     // one process per GPU: the rank's whole iteration (sweep, all-reduce, finish) replays as ONE graph; NCCL calls are capturable
-    if (h->use_graph && h->nccl_in_graph) return graph_sweep(h, 2);
+    if (h->peer_mode || (h->use_graph && h->nccl_in_graph)) return graph_sweep(h, 2);
     if ((st = graph_sweep(h, 0))) return st;
     const ncclResult_t r = ncclAllReduce(h->mom_part.p, h->mom.p, (size_t)h->ne * h->n, ncclDouble, ncclSum, h->comm, h->stream);
     if (r != ncclSuccess) return fail(PBTE_ERR_CUDA, std::string("ncclAllReduce: ") + ncclGetErrorString(r));
@@ -1812,8 +1843,15 @@ int graph_sweep(pbte_handle *h, int mode)
     if (std::getenv("PBTE_TRACE_FILE")) graph_ok = false;  // the traced sweep synchronises and writes a file
 #endif
     auto enqueue_all = [&]() -> int {
-        int rc = enqueue_sweep(h, piv, mode == 1, &launches);
+        int rc = enqueue_sweep(h, piv, mode == 1, &launches, mode == 2 && h->peer_mode);
         if (rc || mode != 2) return rc;
+        if (h->peer_mode)
+        {
+            // the finish step reads the peers' temperature partial sums over NVLink itself: no collective call between the kernels
+            if ((rc = enqueue_finish(h, true, true))) return rc;
+            ++launches;
+            return PBTE_OK;
+        }
         // the temperature moment alone: the next sweep and the stop test need nothing else (complete_moments brings the rest)
         const ncclResult_t r = ncclAllReduce(h->mom_part.p, h->mom.p, (size_t)h->ne * h->n, ncclDouble, ncclSum, h->comm, h->stream);
         if (r != ncclSuccess) return fail(PBTE_ERR_CUDA, std::string("ncclAllReduce: ") + ncclGetErrorString(r));
@@ -1909,8 +1947,17 @@ int solve_handles(pbte_handle **hs, int nh, int32_t max_iter, double tol, int32_
     {
         while (enq < max_iter && enq - seen < look && st == PBTE_OK)
         {
-            // sweeps of all handles, then their all-reduces as one NCCL group, then the finish steps
-            if (nh > 1)
+            // sweeps of all handles, then their all-reduces as one NCCL group, then the finish steps (peer mode: every handle's
+            // whole iteration is enqueued at once, the finish kernels read each other's partial sums over NVLink)
+            if (nh > 1 && hs[0]->peer_mode)
+            {
+                for (int i = 0; i < nh && st == PBTE_OK; ++i)
+                {
+                    DeviceGuard guard(hs[i]->device);
+                    st = graph_sweep(hs[i], 2);
+                }
+            }
+            else if (nh > 1)
             {
                 for (int i = 0; i < nh && st == PBTE_OK; ++i)
                 {
@@ -2111,6 +2158,139 @@ int pbte_cuda_comm_get_unique_id(void *id)
     return PBTE_OK;
 }
 
+// Exchange buffers for the temperature partial sums and their mapping into every rank (csrc/tail.cuh).  local: all handles live in
+// this process (direct pointers after cudaDeviceEnablePeerAccess); otherwise the buffers are shared as CUDA IPC handles, which the
+// ranks exchange with an ncclAllGather.  Any failure leaves peer_mode off: the all-reduce stays an NCCL call.
+static int alloc_exchange(pbte_handle *h)
+{
+    const size_t xrow = (size_t)h->ne * h->np;
+    CK(h->xchg.alloc(2 * xrow + 16));
+    CK(cudaMemsetAsync(h->xchg.p, 0, h->xchg.count * sizeof(double), h->stream));
+    CK(h->xchg_epoch.alloc(1));
+    CK(cudaMemsetAsync(h->xchg_epoch.p, 0, sizeof(long long), h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return PBTE_OK;
+}
+
+static bool peer_allowed()
+{
+    const char *ev = std::getenv("PBTE_PEER_ALLREDUCE");
+    return !(ev && std::atoi(ev) == 0);
+}
+
+static int enable_peer_ipc(pbte_handle *h)
+{
+    h->peer_mode = false;
+    if (!peer_allowed() || h->comm_size < 2 || h->comm_size > kTailThreads) return PBTE_OK;
+    int st = alloc_exchange(h);
+    if (st) return st;
+    const int n = h->comm_size;
+    cudaIpcMemHandle_t mine;
+    int ok = cudaIpcGetMemHandle(&mine, h->xchg.p) == cudaSuccess ? 1 : 0;
+    (void)cudaGetLastError();
+    // handles of all ranks (an all-gather of 64 bytes + 1 validity byte per rank through NCCL: device buffers)
+    const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
+    DevBuf<unsigned char> d_all;
+    CK(d_all.alloc(rec * n));
+    std::vector<unsigned char> rec_mine(rec, 0), all(rec * n, 0);
+    std::memcpy(rec_mine.data(), &mine, sizeof(mine));
+    rec_mine[sizeof(mine)] = (unsigned char)ok;
+    CK(cudaMemcpyAsync(d_all.p + rec * h->comm_rank, rec_mine.data(), rec, cudaMemcpyHostToDevice, h->stream));
+    const ncclResult_t r = ncclAllGather(d_all.p + rec * h->comm_rank, d_all.p, rec, ncclUint8, h->comm, h->stream);
+    if (r != ncclSuccess) return fail(PBTE_ERR_CUDA, std::string("ncclAllGather: ") + ncclGetErrorString(r));
+    CK(cudaMemcpyAsync(all.data(), d_all.p, rec * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    bool all_ok = true;
+    for (int k = 0; k < n; ++k) all_ok = all_ok && all[rec * k + sizeof(mine)] == 1;
+    std::vector<const double *> peers(n, nullptr);
+    int opened_ok = all_ok ? 1 : 0;
+    if (all_ok)
+        for (int k = 0; k < n; ++k)
+        {
+            if (k == h->comm_rank)
+            {
+                peers[k] = h->xchg.p;
+                continue;
+            }
+            cudaIpcMemHandle_t hk;
+            std::memcpy(&hk, all.data() + rec * k, sizeof(hk));
+            void *ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, hk, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+            {
+                (void)cudaGetLastError();
+                opened_ok = 0;
+                break;
+            }
+            h->ipc_opened.push_back(ptr);
+            peers[k] = static_cast<const double *>(ptr);
+        }
+    // every rank must have mapped every buffer, or nobody uses them (one more tiny collective: min over the ranks)
+    DevBuf<int> d_flag;
+    CK(d_flag.alloc(1));
+    CK(cudaMemcpyAsync(d_flag.p, &opened_ok, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    const ncclResult_t r2 = ncclAllReduce(d_flag.p, d_flag.p, 1, ncclInt, ncclMin, h->comm, h->stream);
+    if (r2 != ncclSuccess) return fail(PBTE_ERR_CUDA, std::string("ncclAllReduce: ") + ncclGetErrorString(r2));
+    int agreed = 0;
+    CK(cudaMemcpyAsync(&agreed, d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (agreed != 1)
+    {
+        for (void *q : h->ipc_opened) cudaIpcCloseMemHandle(q);
+        h->ipc_opened.clear();
+        (void)cudaGetLastError();
+        return PBTE_OK;
+    }
+    if ((st = upload(h->d_peers, peers.data(), peers.size(), h->stream))) return st;
+    CK(cudaStreamSynchronize(h->stream));
+    h->peer_mode = true;
+    return PBTE_OK;
+}
+
+static int enable_peer_local(pbte_handle *const *hs, int n)
+{
+    for (int i = 0; i < n; ++i) hs[i]->peer_mode = false;
+    if (!peer_allowed() || n < 2 || n > kTailThreads) return PBTE_OK;
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j)
+        {
+            if (i == j) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, hs[i]->device, hs[j]->device) != cudaSuccess || !can)
+            {
+                (void)cudaGetLastError();
+                return PBTE_OK;
+            }
+        }
+    std::vector<const double *> peers(n, nullptr);
+    for (int i = 0; i < n; ++i)
+    {
+        DeviceGuard guard(hs[i]->device);
+        for (int j = 0; j < n; ++j)
+            if (j != i)
+            {
+                const cudaError_t e = cudaDeviceEnablePeerAccess(hs[j]->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                {
+                    (void)cudaGetLastError();
+                    return PBTE_OK;
+                }
+                (void)cudaGetLastError();
+            }
+        const int st = alloc_exchange(hs[i]);
+        if (st) return st;
+        peers[i] = hs[i]->xchg.p;
+    }
+    for (int i = 0; i < n; ++i)
+    {
+        DeviceGuard guard(hs[i]->device);
+        const int st = upload(hs[i]->d_peers, peers.data(), peers.size(), hs[i]->stream);
+        if (st) return st;
+        CK(cudaStreamSynchronize(hs[i]->stream));
+    }
+    for (int i = 0; i < n; ++i) hs[i]->peer_mode = true;
+    return PBTE_OK;
+}
+
 static int after_attach(pbte_handle *h)
 {
     h->drop_graphs();
@@ -2138,7 +2318,8 @@ int pbte_cuda_comm_attach(pbte_handle_t *h, const void *id, int32_t rank, int32_
     }
     h->comm_rank = rank;
     h->comm_size = world_size;
-    return after_attach(h);
+    if ((st = after_attach(h))) return st;
+    return enable_peer_ipc(h);
 }
 
 int pbte_cuda_comm_attach_all(pbte_handle_t *const *handles, int32_t n)
@@ -2166,7 +2347,7 @@ int pbte_cuda_comm_attach_all(pbte_handle_t *const *handles, int32_t n)
         const int st = after_attach(handles[i]);
         if (st) return st;
     }
-    return PBTE_OK;
+    return enable_peer_local(handles, n);
 }
 
 int pbte_cuda_comm_detach(pbte_handle_t *h)
@@ -2179,6 +2360,10 @@ int pbte_cuda_comm_detach(pbte_handle_t *h)
     h->comm = nullptr;
     h->comm_rank = 0;
     h->comm_size = 1;
+    for (void *q : h->ipc_opened) cudaIpcCloseMemHandle(q);
+    h->ipc_opened.clear();
+    h->peer_mode = false;
+    h->xchg.release();
     h->mom_part.release();
     h->drop_graphs();
     return PBTE_OK;

@@ -43,7 +43,28 @@ struct DevTail
     double *block_part;    // [gridDim.x][3]
     DevCtrl *ctrl;
     double *hist;          // device view of the pinned history ring [kHistRing][4]
+    // Multi-GPU exchange over NVLink peer memory (instead of an NCCL all-reduce between the two kernels):
+    //   peer = 1 (tail of a sweep): the temperature partial sums go into this rank's exchange buffer xchg[parity][ne][np]; the last
+    //            CTA publishes epoch + 1 in the flag behind it (release at system scope);
+    //   peer = 2 (finish): waits until every peer has published epoch + 1, adds the N partial buffers in rank order straight from the
+    //            peers' memory (P2P loads, identical order on every rank: identical sums), and finishes the iteration.
+    // The buffers alternate with the parity of the epoch, so a rank one iteration ahead never overwrites what a peer still reads.
+    int peer, nranks, rank;
+    double *xchg;                   // this rank's buffer: 2 * ne * np doubles, then the flag (long long)
+    const double *const *peers;     // [nranks] every rank's buffer as mapped here (cudaIpcOpenMemHandle / peer access)
+    long long *epoch;               // iterations exchanged so far (device counter, never reset; advanced by the finish step)
 };
+
+__device__ __forceinline__ long long ld_acquire_sys(const long long *p)
+{
+    long long v;
+    asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(long long *p, long long v)
+{
+    asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
 __device__ __forceinline__ bool last_arrival(unsigned *ticket, unsigned expected, int *s_flag)
 {
@@ -138,6 +159,32 @@ __global__ void __launch_bounds__(kTailThreads, PBTE_TAIL_MINBLOCKS) iteration_t
             if (!last_arrival(Z.tickets + blockIdx.x, (unsigned)Z.nparts, &s_flag)) return;
         }
     }
+    // ---- multi-GPU: wait for the peers' partial sums of this iteration ------------------------------------------------------------
+    const size_t xrow = (size_t)ne * np;  // doubles per exchange buffer
+    long long ep = 0;
+    if (Z.peer)
+    {
+        ep = *Z.epoch;
+        if (Z.peer == 2)
+        {
+            if (t < Z.nranks && t != Z.rank)
+            {
+                const long long *flag = reinterpret_cast<const long long *>(Z.peers[t] + 2 * xrow);
+                const long long t0 = clock64();
+                while (ld_acquire_sys(flag) < ep + 1)
+                {
+                    __nanosleep(200);
+                    if (clock64() - t0 > 20000000000LL)
+                    {
+                        // a peer that never arrives (its process died): give up loudly instead of hanging the GPU
+                        atomicCAS(P.error_flag, 0, PBTE_ERR_CUDA);
+                        break;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
     // ---- sum of the partial vectors, ascending (fixed order) ---------------------------------------------------------------
     if (valid)
     {
@@ -150,7 +197,21 @@ __global__ void __launch_bounds__(kTailThreads, PBTE_TAIL_MINBLOCKS) iteration_t
                 if (m >= nm) break;
                 if (nparts == 0 && (m < Z.m_begin || m >= Z.m_end)) continue;
                 double a = 0.0, b = 0.0;
-                if (nparts == 0)
+                if (nparts == 0 && Z.peer == 2 && m == 0)
+                {
+                    // the N ranks' partial sums in rank order, straight from their memory (uncached: the buffers are rewritten every
+                    // other iteration); the all-reduced row also goes to the local moment vector
+                    const size_t off = (size_t)(ep & 1) * xrow + (size_t)e * np + i0;
+                    for (int rk = 0; rk < Z.nranks; ++rk)
+                    {
+                        const double2 w = __ldcv(reinterpret_cast<const double2 *>(Z.peers[rk] + off));
+                        a += w.x;
+                        b += w.y;
+                    }
+                    Z.mom[x0] = a;
+                    if (has1) Z.mom[x0 + 1] = b;
+                }
+                else if (nparts == 0)
                 {
                     a = Z.mom[(size_t)m * block + x0];
                     if (has1) b = Z.mom[(size_t)m * block + x0 + 1];
@@ -170,11 +231,29 @@ __global__ void __launch_bounds__(kTailThreads, PBTE_TAIL_MINBLOCKS) iteration_t
             for (int m = 0; m <= kMaxDim; ++m)
             {
                 if (m >= nm) break;
+                if (m == 0 && Z.peer == 1)
+                {
+                    // temperature partial sums of this rank: into the exchange buffer the peers read (padded rows: 16-byte stores)
+                    *reinterpret_cast<double2 *>(Z.xchg + (size_t)(ep & 1) * xrow + (size_t)e * np + i0) = make_double2(v[0][0], has1 ? v[0][1] : 0.0);
+                    continue;
+                }
                 Z.mom[(size_t)m * block + x0] = v[m][0];
                 if (has1) Z.mom[(size_t)m * block + x0 + 1] = v[m][1];
             }
     }
-    if (!Z.finish) return;
+    if (!Z.finish)
+    {
+        if (Z.peer == 1)
+        {
+            // publish: the last CTA of the grid (every CTA that reaches this point has written its rows) releases the flag
+            if (last_arrival(Z.tickets + gridDim.x, gridDim.x, &s_flag) && t == 0)
+            {
+                __threadfence_system();
+                st_release_sys(reinterpret_cast<long long *>(Z.xchg + 2 * xrow), ep + 1);
+            }
+        }
+        return;
+    }
 
     // ---- finish: cell integrals, norms, hand-over ----------------------------------------------------------------------------
     const int mb = Z.m_begin, me = min(Z.m_end, nm);
@@ -271,6 +350,7 @@ __global__ void __launch_bounds__(kTailThreads, PBTE_TAIL_MINBLOCKS) iteration_t
         h[2] = tot[2];
         h[3] = (double)*P.error_flag;
         c->iter = it + 1;
+        if (Z.peer == 2) *Z.epoch = ep + 1;
         // the reference's stop test: res = ||Tv - Tv_prev|| / ||Tv|| < tol (src/PBTESolver.cpp:327)
         if (tot[1] > 0.0 && sqrt(tot[0]) / sqrt(tot[1]) < c->tol) c->stop = 1;
         __threadfence_system();
