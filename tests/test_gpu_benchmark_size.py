@@ -131,11 +131,14 @@ def test_c5_one_level_down_vs_oracle(variant, monkeypatch):
     hc.close()
 
 
-def test_two_devices_equal_one_device(c2_consistent):
-    """Two handles on two GPUs of one process, directions split in halves, the all-reduce issued by the library (NCCL):
-    same iterates as one handle on one GPU (the sum order of the moments differs: 1e-13)."""
+@pytest.mark.parametrize("peer", ["1", "0"])
+def test_two_devices_equal_one_device(c2_consistent, peer, monkeypatch):
+    """Two handles on two GPUs of one process, directions split in halves, the exchange done by the library — over NVLink peer memory
+    inside the finish kernel (peer = 1, the default) or as an NCCL all-reduce (PBTE_PEER_ALLREDUCE=0): same iterates as one handle on
+    one GPU (the sum order of the moments differs: 1e-13)."""
     if pb.device_count() < 2:
         pytest.skip("needs two CUDA devices")
+    monkeypatch.setenv("PBTE_PEER_ALLREDUCE", peer)
     P = c2_consistent.problem  # well-conditioned local systems: the two summation orders agree to rounding
     one = pb.Solver(P, device=0)
     one.build_schedule()
