@@ -915,13 +915,16 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
     h->march_max_class_tiles = sched.max_class_tiles;
     // shared memory of a marching CTA: operators (staged when they fit) + metadata/barriers + tile ring.  Two CTAs per SM when
     // that leaves room for a ring of >= 6 tiles each, one CTA otherwise; without room for operators they are read through L1.
-    h->march_nv = 2 + sched.max_inflow;
+    // staged vectors per ring slot: u_old, T_old and one per inflow face; the kernels whose source producer forms X = c1 T_old + c2 u_old
+    // itself (march_xsrc) stage one vector less.  The register-operator kernel keeps the two source vectors.
+    const int nv_regop = 2 + sched.max_inflow, nv_march = (march_xsrc(n) ? 1 : 2) + sched.max_inflow;
+    h->march_nv = nv_march;
     const size_t h_all = (size_t)noc * F * n;
     // PBTE_MARCH_NOSTAGE=1 forces the large-mesh code path (operators and wall vectors read through L1 instead of staged)
     const bool allow_stage = !(std::getenv("PBTE_MARCH_NOSTAGE") && std::atoi(std::getenv("PBTE_MARCH_NOSTAGE")) != 0);
     h->march_h_smem = allow_stage && h_all * sizeof(double) <= 16 * 1024;
     const size_t h_doubles = h->march_h_smem ? h_all : 0;
-    const size_t slot_bytes = march_slot_bytes(n, sched.rows, h->march_nv, F);
+    const size_t slot_bytes = march_slot_bytes(n, sched.rows, nv_march, F), slot_bytes_regop = march_slot_bytes(n, sched.rows, nv_regop, F);
     const size_t sm_total = (size_t)max_optin, sm_half = (228 * 1024) / 2 - 2048;
     // Two kernels walk the tiles (sweep_shared.cuh): the persistent one cuts the slots into equal work lists, which pays when there are
     // more slots than resident CTAs AND its operators are staged (measured, profiles/r02_kernel_probes.txt); otherwise the classic one.
@@ -940,8 +943,10 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
         // warp (ring size a multiple of the producer warps per role: a warp works in order, so the slot's previous tile is loaded
         // before it waits for the slot again) and the ring holds at least one tile per consumer warp (a consumer must find the
         // slot of its next tile at most one phase behind).  A ring that breaks the first rule hangs on large meshes.
-        const int step = march_role_warps(n) % 2 == 0 ? march_role_warps(n) : 2 * march_role_warps(n);
-        const int cap = march_ctas_per_sm(n) == 1 ? 2 * march_consumers(n) + 8 : 16;  // deeper than that returns nothing
+        int step = march_src_warps(n);  // a multiple of both loader-warp counts, and even
+        while (step % march_nbr_warps(n) != 0 || step % 2 != 0) step += march_src_warps(n);
+        int cap = march_ctas_per_sm(n) == 1 ? 2 * march_consumers(n) + 8 : 16;  // deeper than that returns nothing
+        if (const char *ev = std::getenv("PBTE_RING_CAP")) cap = std::max(std::atoi(ev), march_min_ring(n));
         for (int r = cap / step * step; r >= march_min_ring(n) && r > 0; r -= step)
             if (fixed + meta_of(pers, r) + (size_t)r * slot_bytes <= budget)
             {
@@ -965,7 +970,7 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
         {
             const size_t budget = regop_ctas(n) == 2 ? sm_half : sm_total - 1024;
             for (int r = 16; r >= 2 * regop_groups(n) && r >= 4; r -= 2)
-                if (regop_meta_bytes(n, r, h_doubles) + 16 + (size_t)r * slot_bytes <= budget)
+                if (regop_meta_bytes(n, r, h_doubles) + 16 + (size_t)r * slot_bytes_regop <= budget)
                 {
                     h->march_regop = true;
                     ring = r;
@@ -978,7 +983,8 @@ int setup_march(pbte_handle *h, const std::vector<uint8_t> &cin, const std::vect
     if (h->march_regop)
     {
         h->march_stage = false;
-        h->march_smem = regop_meta_bytes(n, ring, h_doubles) + 16 + (size_t)ring * slot_bytes;
+        h->march_smem = regop_meta_bytes(n, ring, h_doubles) + 16 + (size_t)ring * slot_bytes_regop;
+        h->march_nv = nv_regop;
         fn = pick_regop_kernel(n);
     }
     else

@@ -454,8 +454,17 @@ constexpr int kMaxIn = 4;          // inflow faces whose wall temperature a cons
 #ifndef PBTE_SMALL_CTAS
 #define PBTE_SMALL_CTAS 2
 #endif
-__host__ __device__ constexpr int march_consumers(int n) { return n <= 16 ? PBTE_SMALL_CONSUMERS : (n <= 36 ? 8 : 4); }
-__host__ __device__ constexpr int march_ctas_per_sm(int n) { return n <= 16 ? PBTE_SMALL_CTAS : (n <= 36 ? 2 : 1); }
+#ifndef PBTE_MID_CONSUMERS
+#define PBTE_MID_CONSUMERS 8
+#endif
+#ifndef PBTE_MID_CTAS
+#define PBTE_MID_CTAS 2
+#endif
+#ifndef PBTE_MID_PRODUCERS
+#define PBTE_MID_PRODUCERS 2
+#endif
+__host__ __device__ constexpr int march_consumers(int n) { return n <= 16 ? PBTE_SMALL_CONSUMERS : (n <= 36 ? PBTE_MID_CONSUMERS : 4); }
+__host__ __device__ constexpr int march_ctas_per_sm(int n) { return n <= 16 ? PBTE_SMALL_CTAS : (n <= 36 ? PBTE_MID_CTAS : 1); }
 // Consumer warps that share one tile (compile-time experiment, off): with three or four MMA column blocks (ndof 25..36) two warps
 // split the columns — warp 0 the blocks 0 and 1, warp 1 the rest and the DFMA remainder — so a tile leaves its ring slot twice as
 // fast and the eight slots of a CTA hold four tiles in the MMAs and four on their way in.  Measured on C2 (profiles/r02_kernel_probes.txt):
@@ -480,8 +489,14 @@ __host__ __device__ constexpr int march_min_ring(int n) { return march_consumers
 #ifndef PBTE_SMALL_PRODUCERS
 #define PBTE_SMALL_PRODUCERS 4
 #endif
-__host__ __device__ constexpr int march_role_warps(int n) { return n <= 16 ? PBTE_SMALL_PRODUCERS : 2; }
-__host__ __device__ constexpr int march_threads(int n) { return (march_consumers(n) + 2 * march_role_warps(n)) * 32; }
+__host__ __device__ constexpr int march_role_warps(int n) { return n <= 16 ? PBTE_SMALL_PRODUCERS : (n <= 36 ? PBTE_MID_PRODUCERS : 2); }
+// source / neighbour loader warps (the same number of each unless an experiment build says otherwise)
+#ifndef PBTE_MID_NBR
+#define PBTE_MID_NBR PBTE_MID_PRODUCERS
+#endif
+__host__ __device__ constexpr int march_src_warps(int n) { return march_role_warps(n); }
+__host__ __device__ constexpr int march_nbr_warps(int n) { return (n > 16 && n <= 36) ? PBTE_MID_NBR : march_role_warps(n); }
+__host__ __device__ constexpr int march_threads(int n) { return (march_consumers(n) + march_src_warps(n) + march_nbr_warps(n)) * 32; }
 
 // shared-memory row stride (doubles) of a staged element vector: 4*KS rounded so that the four element rows a half warp reads
 // with one LDS.64 fall into disjoint bank groups (stride mod 16 in {4, 12})
@@ -495,6 +510,148 @@ __host__ __device__ inline size_t march_slot_bytes(int n, int rows, int nv, int 
 {
     return (size_t)rows * 32 + (size_t)kTile * ((F + 1) & ~1) * sizeof(double) + (size_t)nv * kTile * stage_stride(n) * sizeof(double);
 }
+// ---------------------------------------------------------------------------------------------------------------
+// REGISTER-STAGED PRODUCERS (round 2, late).  With a ring slot per consumer warp a freed slot is the start of a latency chain:
+// cp.async issued after the slot frees lands 700 - 1500 cycles later, and the ncu source page of the C2 kernel showed the consumers
+// waiting for a full slot 36 % of their time.  Rows of at most 16 chunks (ndof <= 32) are therefore loaded into REGISTERS while the
+// producer still waits for the slot (the loads need no slot, only their stores do); when the slot frees, the warp stores them to
+// shared memory and arrives: the chain shrinks to a few store instructions.  The source producer forms X = c1 T_old + c2 u_old on
+// the way (same expression, same rounding as the consumers used to evaluate per A fragment), so T_old needs no staged vector (one
+// vector less per slot: the C2 ring grows from 8 to 10 tiles) and the first matrix block of a tile is a plain block like the others.
+#ifndef PBTE_XSRC
+#define PBTE_XSRC 0  // measured (profiles/r02_kernel_probes.txt, runs q and r): a source warp then has ONE tile in flight instead of a ring of
+                     // them and pays the HBM latency per tile (C2 0.406 against 0.367 ms, C5 slice 2.78 against 1.98 ms); with the neighbour
+                     // rows in registers as well ptxas funnels the twelve 16-byte loads of a hex tile through one register quad (0.75 - 0.92 ms)
+#endif
+__host__ __device__ constexpr bool march_xsrc(int n) { return PBTE_XSRC != 0 && ((n + 1) & ~1) <= 32; }
+#ifndef PBTE_XNBR
+#define PBTE_XNBR 1  // 0: only the source producer goes through registers, the neighbour rows stay cp.async (issued when the slot frees)
+#endif
+__host__ __device__ constexpr bool march_xnbr(int n) { return march_xsrc(n) && PBTE_XNBR != 0; }
+constexpr int kRegFaces = 3;  // inflow faces whose rows one register-staged pass of the neighbour producer holds (tri/quad 2, tet/hex 3)
+
+// 16-byte load through L2 (rows written by other warps / CTAs during this sweep must not come from L1); predicated INSIDE the asm
+// so that every load keeps its own destination registers (a select around the asm made ptxas funnel all loads of a tile through one
+// register pair, one L2 round trip after the other); `ok` false leaves zeros
+__device__ __forceinline__ double2 ld_cg_f64x2_if(const void *p, bool ok)
+{
+    double2 v = make_double2(0.0, 0.0);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %3, 0;\n"
+        "@p ld.global.cg.v2.f64 {%0, %1}, [%2];\n"
+        "}\n"
+        : "+d"(v.x), "+d"(v.y)
+        : "l"(p), "r"((int)ok)
+        : "memory");
+    return v;
+}
+// the same with two 8-byte loads: 12 in-flight 16-byte loads per lane (the neighbour rows of a hex tile) need 12 aligned register
+// quads, which ptxas only finds by funnelling every load through one temporary quad - pairs it does find
+__device__ __forceinline__ double2 ld_cg_f64_f64_if(const void *p, bool ok)
+{
+    double2 v = make_double2(0.0, 0.0);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %3, 0;\n"
+        "@p ld.global.cg.f64 %0, [%2];\n"
+        "@p ld.global.cg.f64 %1, [%2+8];\n"
+        "}\n"
+        : "+d"(v.x), "+d"(v.y)
+        : "l"(p), "r"((int)ok)
+        : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_shared_f64x2(uint32_t addr, double2 v)
+{
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ void st_shared_u32x4(uint32_t addr, uint4 v)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// Source producer, one tile: lane q = lane & 7 holds element q of the tile in `e` (-1: padding).  u/tc: slot's flux and T_old, row
+// stride NP.  sl: the ring slot; the slot must be free before the stores (wait_empty: parity wait on empty_bar).
+template <int N>
+__device__ __forceinline__ void src_tile_regs(const double *u, const double *tc, int e, const int32_t *desc_g, const double *ctbc, int rows, int Fp,
+                                              double c1, double c2, unsigned char *sl, size_t hdr_bytes, uint64_t *empty_bar, bool wait_empty,
+                                              uint32_t parity, uint64_t *full_bar)
+{
+    constexpr int NP = (N + 1) & ~1, NS = stage_stride(N), CH = NP / 2, RPI = 32 / CH, IT = (kTile + RPI - 1) / RPI;
+    const int lane = threadIdx.x & 31, r_sub = lane / CH, lch = lane - r_sub * CH;
+    const bool lane_copies = r_sub < RPI;
+    double2 ru[IT], rt[IT];
+#pragma unroll
+    for (int k = 0; k < IT; ++k)
+    {
+        const int row = k * RPI + r_sub;
+        const int er = __shfl_sync(0xffffffffu, e, row & 7);
+        const bool ok = lane_copies && row < kTile && er >= 0;
+        const size_t off = (size_t)(er < 0 ? 0 : er) * NP + 2 * lch;
+        ru[k] = ld_cg_f64x2_if(u + off, ok);
+        rt[k] = ok ? __ldg(reinterpret_cast<const double2 *>(tc + off)) : make_double2(0.0, 0.0);
+    }
+    uint4 dsc = make_uint4(0, 0, 0, 0);
+    if (lane < rows * 2) dsc = __ldg(reinterpret_cast<const uint4 *>(desc_g) + lane);
+    // wall temperatures of the 8 elements: Fp/2 chunks per row (at most 32 chunks in all)
+    const int hc = Fp >> 1, wrow = lane / hc, wch = lane - wrow * hc;
+    const int ew = __shfl_sync(0xffffffffu, e, wrow & 7);
+    double2 wt = make_double2(0.0, 0.0);
+    if (lane < kTile * hc && ew >= 0) wt = __ldg(reinterpret_cast<const double2 *>(ctbc + (size_t)ew * Fp + 2 * wch));
+    if (wait_empty) mbar_wait(empty_bar, parity);
+    const uint32_t sb = smem_u32(sl);
+    const uint32_t vb = sb + (uint32_t)hdr_bytes + (uint32_t)(r_sub * NS * 8 + lch * 16);
+#pragma unroll
+    for (int k = 0; k < IT; ++k)
+    {
+        const int row = k * RPI + r_sub;
+        if (lane_copies && row < kTile)
+            st_shared_f64x2(vb + (uint32_t)(k * RPI * NS * 8), make_double2(fma(c2, ru[k].x, c1 * rt[k].x), fma(c2, ru[k].y, c1 * rt[k].y)));
+    }
+    if (lane < rows * 2) st_shared_u32x4(sb + lane * 16, dsc);
+    if (lane < kTile * hc) st_shared_f64x2(sb + rows * 32 + lane * 16, wt);
+    mbar_arrive(full_bar);  // release: this lane's stores are visible to whoever acquires the completed phase
+}
+
+// Neighbour producer, one tile whose prerequisites are stored: lane (mq, q) = (lane >> 3, lane & 7) holds in `code0` the source row of
+// face mq, element q (negative: wall / no neighbour -> zeros).  first_vec: index of face 0's staged vector in the slot.
+template <int N>
+__device__ __forceinline__ void nbr_tile_regs(const double *u, int code0, int nin, const int32_t *desc_g, int first_vec, unsigned char *sl,
+                                              size_t hdr_bytes, uint64_t *empty_bar, bool wait_empty, uint32_t parity, uint64_t *full_bar)
+{
+    constexpr int NP = (N + 1) & ~1, NS = stage_stride(N), CH = NP / 2, RPI = 32 / CH, IT = (kRegFaces * kTile + RPI - 1) / RPI;
+    const int lane = threadIdx.x & 31, r_sub = lane / CH, lch = lane - r_sub * CH, q = lane & 7, mq = lane >> 3;
+    const bool lane_copies = r_sub < RPI;
+    const uint32_t vb0 = smem_u32(sl) + (uint32_t)hdr_bytes + (uint32_t)(r_sub * NS * 8 + lch * 16);
+    for (int m0 = 0; m0 < nin; m0 += kRegFaces)
+    {
+        const int code = m0 == 0 ? code0 : ((mq < kRegFaces && m0 + mq < nin) ? __ldg(desc_g + (1 + m0 + mq) * kTile + q) : kSrcSkipCode);
+        const int nrow = min(nin - m0, kRegFaces) * kTile;
+        double2 rv[IT];
+#pragma unroll
+        for (int k = 0; k < IT; ++k)
+        {
+            const int row = k * RPI + r_sub;  // lane `row` holds the source of row `row` (face m0 + row / 8, element row % 8)
+            const int cr = __shfl_sync(0xffffffffu, code, row & 31);
+            if constexpr (IT > 8) rv[k] = ld_cg_f64_f64_if(u + (size_t)(cr < 0 ? 0 : cr) * NP + 2 * lch, lane_copies && row < nrow && cr >= 0);
+            else rv[k] = ld_cg_f64x2_if(u + (size_t)(cr < 0 ? 0 : cr) * NP + 2 * lch, lane_copies && row < nrow && cr >= 0);
+        }
+        if (wait_empty && m0 == 0) mbar_wait(empty_bar, parity);
+        const uint32_t vb = vb0 + (uint32_t)((first_vec + m0) * kTile * NS * 8);
+#pragma unroll
+        for (int k = 0; k < IT; ++k)
+        {
+            const int row = k * RPI + r_sub;
+            if (lane_copies && row < nrow) st_shared_f64x2(vb + (uint32_t)(k * RPI * NS * 8), rv[k]);
+        }
+    }
+    if (wait_empty && nin == 0) mbar_wait(empty_bar, parity);
+    mbar_arrive(full_bar);
+}
+
 // bytes of metadata and barriers: inflow masks, operator offsets; full/empty per ring slot; the bitmap of finished tiles; h_doubles
 // wall-vector entries staged when they fit
 __host__ __device__ inline size_t march_meta_bytes(int noclass, int ring, int max_class_tiles, size_t h_doubles, int wpt)
@@ -540,7 +697,7 @@ template <int N, bool STAGE>
 __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_march_kernel(DevProblem P, DevMarch S)
 {
     constexpr int kConsumerWarps = march_consumers(N);
-    constexpr int kSrcWarps = march_role_warps(N), kNbrWarps = march_role_warps(N);
+    constexpr int kSrcWarps = march_src_warps(N), kNbrWarps = march_nbr_warps(N);
     using G = Split<N, STAGE>;
     constexpr int MTM = G::MTM, REM = G::REM, REMP = G::REMP, P2 = G::P2, KS = G::KS, MAIN = G::MAIN;
     constexpr int OPS = STAGE ? G::OPS : compact_doubles(N);  // doubles per operator: staged operators are in split order, others compact
@@ -644,6 +801,7 @@ __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_
             const int q = lane & 7;  // lanes 0-7 hold the elements of the u_old rows, lanes 8-15 the same elements for the T_old rows
             const int first = (warp - kConsumerWarps - gbase % kSrcWarps + kSrcWarps) % kSrcWarps;
             int e_next = first < ntile ? __ldg(desc0 + (size_t)first * rows * kTile + q) : -1;
+            int slot = (gbase + first) % R, it = (gbase + first) / R;  // carried along: R is a run-time value, a division per tile is not free
             // Experiment (off): the ring cannot run far ahead of the consumers (a slot per consumer warp), so the u_old rows of a tile come
             // from HBM at the moment its slot frees; pull the rows of the tile kPrefetchAhead tiles further on into L2 now (one 128-byte
             // line per lane: 8 rows x 2 lines).
@@ -652,12 +810,21 @@ __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_
 #endif
             constexpr int kPrefetchAhead = PBTE_L2_PREFETCH;
             [[maybe_unused]] int e_pf = (kPrefetchAhead > 0 && first + kPrefetchAhead < ntile) ? __ldg(desc0 + (size_t)(first + kPrefetchAhead) * rows * kTile + q) : -1;
-            for (int j = first; j < ntile; j += kSrcWarps)
+            [[maybe_unused]] const double xc1 = P.slot_c1[s], xc2 = P.slot_c2[s];
+            for (int j = first; j < ntile; j += kSrcWarps, slot += kSrcWarps)
             {
-                const int g = gbase + j, slot = g % R, it = g / R;
+                if (slot >= R) slot -= R, ++it;
                 const int e = e_next;
                 const int32_t *desc_g = desc0 + (size_t)j * rows * kTile;
                 if (j + kSrcWarps < ntile) e_next = __ldg(desc_g + (size_t)kSrcWarps * rows * kTile + q);
+                if constexpr (march_xsrc(N))
+                {
+                    src_tile_regs<N>(u, P.tc_prev, e, desc_g, S.ctbc, rows, Fp, xc1, xc2, ring + (size_t)slot * slot_bytes, hdr_bytes, empty + slot,
+                                     it > 0, (uint32_t)(it - 1) & 1u, full + slot);
+                    PBTE_STAMP(t0 + j, 8);
+                }
+                else
+                {
                 if constexpr (kPrefetchAhead > 0)
                 {
                     const int ep = __shfl_sync(0xffffffffu, e_pf, lane >> 1);  // lanes 2q, 2q+1: the two lines of row q
@@ -669,15 +836,18 @@ __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_
                 unsigned char *sl = ring + (size_t)slot * slot_bytes;
                 PBTE_STAMP(t0 + j, 7);
                 const uint32_t vb = smem_u32(sl + hdr_bytes) + lane_off;
+                // all shuffles first, then all copies: a copy that waits for its own shuffle runs at the shuffle latency
+                int er[ITS];
+#pragma unroll
+                for (int k = 0; k < ITS; ++k) er[k] = __shfl_sync(0xffffffffu, e, (k * RPI + r_sub) & 7);
 #pragma unroll
                 for (int k = 0; k < ITS; ++k)
                 {
                     const int row = k * RPI + r_sub;  // rows 0-7 u_old, 8-15 T_old of the tile's elements
-                    const int er = __shfl_sync(0xffffffffu, e, row & 7);
                     if (lane_copies && row < 16)
                     {
-                        const unsigned char *src = (row < 8 ? ub : tb) + (size_t)(er < 0 ? 0 : er) * (NP * 8);
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vb + (uint32_t)(k * RPI * NS * 8)), "l"(src), "r"(er >= 0 ? 16u : 0u) : "memory");
+                        const unsigned char *src = (row < 8 ? ub : tb) + (size_t)(er[k] < 0 ? 0 : er[k]) * (NP * 8);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vb + (uint32_t)(k * RPI * NS * 8)), "l"(src), "r"(er[k] >= 0 ? 16u : 0u) : "memory");
                     }
                 }
                 if (lane < rows * 2) cp_async16(sl + lane * 16, reinterpret_cast<const unsigned char *>(desc_g) + lane * 16, 16u);
@@ -690,6 +860,7 @@ __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_
                 }
                 cp_async_arrive(full + slot);
                 PBTE_STAMP(t0 + j, 8);
+                }
             }
         }
         else if (warp >= kConsumerWarps + kSrcWarps)
@@ -701,11 +872,12 @@ __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_
             int wm = t0;  // watermark: tiles [0, wm) of this slot are known to be stored
             const int first = (warp - kConsumerWarps - kSrcWarps - gbase % kNbrWarps + kNbrWarps) % kNbrWarps;
             const int32_t *d0 = desc0 + (size_t)first * rows * kTile;
+            int slot = (gbase + first) % R, it = (gbase + first) / R;
             int o_next = first < ntile ? __ldg(d0 + (1 + F) * kTile) : 0, L_next = first < ntile ? __ldg(d0 + (1 + F) * kTile + 3) : -1;
             int code_next = first < ntile ? __ldg(d0 + (1 + mq) * kTile + q) : -1;  // rows 1..4 always exist (rows = 2 + F, F >= 3)
-            for (int j = first; j < ntile; j += kNbrWarps)
+            for (int j = first; j < ntile; j += kNbrWarps, slot += kNbrWarps)
             {
-                const int g = gbase + j, slot = g % R, it = g / R;
+                if (slot >= R) slot -= R, ++it;
                 const int o = o_next, dep = L_next, code0 = code_next;
                 const int32_t *desc_g = desc0 + (size_t)j * rows * kTile;
                 if (j + kNbrWarps < ntile)
@@ -715,7 +887,8 @@ __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_
                     L_next = __ldg(dn + (1 + F) * kTile + 3);
                     code_next = __ldg(dn + (1 + mq) * kTile + q);
                 }
-                if (it > 0) mbar_wait(empty + slot, (it - 1) & 1);
+                if constexpr (!march_xnbr(N))
+                    if (it > 0) mbar_wait(empty + slot, (it - 1) & 1);
                 PBTE_STAMP(t0 + j, 4);
                 // every tile up to the last prerequisite must be stored: advance the watermark over the bitmap of finished tiles
 #ifdef PBTE_NODEP  // timing experiment only (wrong results): how fast is the pipeline when no tile waits for another?
@@ -734,27 +907,37 @@ __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_
                 PBTE_STAMP(t0 + j, 5);
                 const int nin = __popc((unsigned)s_inm[o]);
                 unsigned char *sl = ring + (size_t)slot * slot_bytes;
+                if constexpr (march_xnbr(N))
+                {
+                    // rows into registers now, into the slot once it is free
+                    nbr_tile_regs<N>(u, code0, nin, desc_g, 1, sl, hdr_bytes, empty + slot, it > 0, (uint32_t)(it - 1) & 1u, full + slot);
+                    PBTE_STAMP(t0 + j, 6);
+                }
+                else
+                {
                 for (int m0 = 0; m0 < nin; m0 += 4)
                 {
                     // lane (mq, q) holds the source code of row mq*8 + q of this pass
                     const int code = m0 == 0 ? code0 : ((m0 + mq < nin) ? __ldg(desc_g + (1 + m0 + mq) * kTile + q) : kSrcSkipCode);
                     const int nrow = min(nin - m0, 4) * kTile;
-                    const uint32_t vb = smem_u32(sl + hdr_bytes) + (uint32_t)((2 + m0) * kTile * NS * 8) + lane_off;
+                    const uint32_t vb = smem_u32(sl + hdr_bytes) + (uint32_t)(((march_xsrc(N) ? 1 : 2) + m0) * kTile * NS * 8) + lane_off;
+                    int cr[ITN];
+#pragma unroll
+                    for (int k = 0; k < ITN; ++k) cr[k] = __shfl_sync(0xffffffffu, code, (k * RPI + r_sub) & 31);
 #pragma unroll
                     for (int k = 0; k < ITN; ++k)
                     {
-                        if (k * RPI >= nrow) break;
                         const int row = k * RPI + r_sub;  // lane `row` holds the source of row `row` (face m0 + row / 8, element row % 8)
-                        const int cr = __shfl_sync(0xffffffffu, code, row & 31);
                         if (lane_copies && row < nrow)
                         {
-                            const unsigned char *src = ub + (size_t)(cr < 0 ? 0 : cr) * (NP * 8);
-                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vb + (uint32_t)(k * RPI * NS * 8)), "l"(src), "r"(cr >= 0 ? 16u : 0u) : "memory");
+                            const unsigned char *src = ub + (size_t)(cr[k] < 0 ? 0 : cr[k]) * (NP * 8);
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vb + (uint32_t)(k * RPI * NS * 8)), "l"(src), "r"(cr[k] >= 0 ? 16u : 0u) : "memory");
                         }
                     }
                 }
                 cp_async_arrive(full + slot);
                 PBTE_STAMP(t0 + j, 6);
+                }
             }
         }
         else
@@ -893,9 +1076,11 @@ __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_
                     }
                 };
                 PBTE_STAMP(i, 9);
-                block(0, true, op);  // source / pseudo-time term: X = c1 T_old + c2 u_old (vectors 0 and 1 of the slot)
+                // source / pseudo-time term: X = c1 T_old + c2 u_old, formed here from vectors 0 and 1 of the slot or (march_xsrc) by the producer
+                constexpr int kFaceVec = march_xsrc(N) ? 1 : 2;
+                block(0, !march_xsrc(N), op);
                 for (int m = 0; m < nin; ++m)
-                    if (interior >> m & 1u) block((size_t)(2 + m) * kTile * NS, false, op + (size_t)(1 + m) * OPS);
+                    if (interior >> m & 1u) block((size_t)(kFaceVec + m) * kTile * NS, false, op + (size_t)(1 + m) * OPS);
                 // remainder columns: the four lanes of an element row add their partial sums
 #pragma unroll
                 for (int cc = 0; cc < MYREM; ++cc)
@@ -1069,8 +1254,11 @@ template <int N, bool STAGE>
 __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_march_classic_kernel(DevProblem P, DevMarch S)
 {
     constexpr int kConsumerWarps = march_consumers(N);
-    constexpr int kSrcWarps = march_role_warps(N), kNbrWarps = march_role_warps(N);
-    constexpr bool kPairTiles = false;
+    constexpr int kSrcWarps = march_src_warps(N), kNbrWarps = march_nbr_warps(N);
+#ifndef PBTE_PAIR_TILES
+#define PBTE_PAIR_TILES 0  // experiment: a consumer warp takes two tiles of one operator class per pass, every B fragment feeds two MMAs
+#endif
+    constexpr bool kPairTiles = PBTE_PAIR_TILES != 0;
     using G = Frag<N>;
     constexpr int MT = G::MT, MP = G::MP, KS = G::KS, FR = G::FR;
 #ifndef PBTE_COMPACT_OPS
@@ -1155,25 +1343,38 @@ __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_
         const int q = lane & 7;  // lanes 0-7 hold the elements of the u_old rows, lanes 8-15 the same elements for the T_old rows
         const int first = warp - kConsumerWarps;
         int e_next = first < NT ? __ldg(S.tile_desc + (size_t)(tbase + first) * rows * kTile + q) : -1;
-        for (int i = first; i < NT; i += kSrcWarps)
+        int slot = first % R, it = first / R;  // carried along: R is a run-time value, a division per tile is not free
+        [[maybe_unused]] const double xc1 = P.slot_c1[s], xc2 = P.slot_c2[s];
+        for (int i = first; i < NT; i += kSrcWarps, slot += kSrcWarps)
         {
-            const int slot = i % R, it = i / R;
+            if (slot >= R) slot -= R, ++it;
             const int e = e_next;
             const int32_t *desc_g = S.tile_desc + (size_t)(tbase + i) * rows * kTile;
             if (i + kSrcWarps < NT) e_next = __ldg(desc_g + (size_t)kSrcWarps * rows * kTile + q);
+            if constexpr (march_xsrc(N))
+            {
+                src_tile_regs<N>(u, P.tc_prev, e, desc_g, S.ctbc, rows, Fp, xc1, xc2, ring + (size_t)slot * slot_bytes, hdr_bytes, empty + slot, it > 0,
+                                 (uint32_t)(it - 1) & 1u, full + slot);
+                PBTE_STAMP(i, 8);
+            }
+            else
+            {
             if (it > 0) mbar_wait(empty + slot, (it - 1) & 1);
             unsigned char *sl = ring + (size_t)slot * slot_bytes;
             PBTE_STAMP(i, 7);
             const uint32_t vb = smem_u32(sl + hdr_bytes) + lane_off;
+            // all shuffles first, then all copies: a copy that waits for its own shuffle runs at the shuffle latency
+            int er[ITS];
+#pragma unroll
+            for (int k = 0; k < ITS; ++k) er[k] = __shfl_sync(0xffffffffu, e, (k * RPI + r_sub) & 7);
 #pragma unroll
             for (int k = 0; k < ITS; ++k)
             {
                 const int row = k * RPI + r_sub;  // rows 0-7 u_old, 8-15 T_old of the tile's elements
-                const int er = __shfl_sync(0xffffffffu, e, row & 7);
                 if (lane_copies && row < 16)
                 {
-                    const unsigned char *src = (row < 8 ? ub : tb) + (size_t)(er < 0 ? 0 : er) * (NP * 8);
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vb + (uint32_t)(k * RPI * NS * 8)), "l"(src), "r"(er >= 0 ? 16u : 0u) : "memory");
+                    const unsigned char *src = (row < 8 ? ub : tb) + (size_t)(er[k] < 0 ? 0 : er[k]) * (NP * 8);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vb + (uint32_t)(k * RPI * NS * 8)), "l"(src), "r"(er[k] >= 0 ? 16u : 0u) : "memory");
                 }
             }
             if (lane < rows * 2) cp_async16(sl + lane * 16, reinterpret_cast<const unsigned char *>(desc_g) + lane * 16, 16u);
@@ -1186,6 +1387,7 @@ __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_
             }
             cp_async_arrive(full + slot);
             PBTE_STAMP(i, 8);
+            }
         }
     }
     else if (warp >= kConsumerWarps + kSrcWarps)
@@ -1197,11 +1399,12 @@ __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_
         int wm = 0;  // watermark: tiles [0, wm) of this class are known to be stored
         const int first = warp - kConsumerWarps - kSrcWarps;
         const int32_t *d0 = S.tile_desc + (size_t)(tbase + first) * rows * kTile;
+        int slot = first % R, it = first / R;
         int o_next = first < NT ? __ldg(d0 + (1 + F) * kTile) : 0, L_next = first < NT ? __ldg(d0 + (1 + F) * kTile + 3) : -1;
         int code_next = first < NT ? __ldg(d0 + (1 + mq) * kTile + q) : -1;  // rows 1..4 always exist (rows = 2 + F, F >= 3)
-        for (int i = first; i < NT; i += kNbrWarps)
+        for (int i = first; i < NT; i += kNbrWarps, slot += kNbrWarps)
         {
-            const int slot = i % R, it = i / R;
+            if (slot >= R) slot -= R, ++it;
             const int o = o_next, dep = L_next, code0 = code_next;
             const int32_t *desc_g = S.tile_desc + (size_t)(tbase + i) * rows * kTile;
             if (i + kNbrWarps < NT)
@@ -1211,7 +1414,8 @@ __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_
                 L_next = __ldg(dn + (1 + F) * kTile + 3);
                 code_next = __ldg(dn + (1 + mq) * kTile + q);
             }
-            if (it > 0) mbar_wait(empty + slot, (it - 1) & 1);
+            if constexpr (!march_xnbr(N))
+                if (it > 0) mbar_wait(empty + slot, (it - 1) & 1);
             PBTE_STAMP(i, 4);
             // every tile up to the last prerequisite must be stored: advance the watermark over the bitmap of finished tiles
 #ifdef PBTE_NODEP  // timing experiment only (wrong results): how fast is the pipeline when no tile waits for another?
@@ -1228,27 +1432,37 @@ __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_
             PBTE_STAMP(i, 5);
             const int nin = __popc((unsigned)s_inm[o]);
             unsigned char *sl = ring + (size_t)slot * slot_bytes;
+            if constexpr (march_xnbr(N))
+            {
+                // rows into registers now, into the slot once it is free
+                nbr_tile_regs<N>(u, code0, nin, desc_g, 1, sl, hdr_bytes, empty + slot, it > 0, (uint32_t)(it - 1) & 1u, full + slot);
+                PBTE_STAMP(i, 6);
+            }
+            else
+            {
             for (int m0 = 0; m0 < nin; m0 += 4)
             {
                 // lane (mq, q) holds the source code of row mq*8 + q of this pass
                 const int code = m0 == 0 ? code0 : ((m0 + mq < nin) ? __ldg(desc_g + (1 + m0 + mq) * kTile + q) : kSrcSkipCode);
                 const int nrow = min(nin - m0, 4) * kTile;
-                const uint32_t vb = smem_u32(sl + hdr_bytes) + (uint32_t)((2 + m0) * kTile * NS * 8) + lane_off;
+                const uint32_t vb = smem_u32(sl + hdr_bytes) + (uint32_t)(((march_xsrc(N) ? 1 : 2) + m0) * kTile * NS * 8) + lane_off;
+                int cr[ITN];
+#pragma unroll
+                for (int k = 0; k < ITN; ++k) cr[k] = __shfl_sync(0xffffffffu, code, (k * RPI + r_sub) & 31);
 #pragma unroll
                 for (int k = 0; k < ITN; ++k)
                 {
-                    if (k * RPI >= nrow) break;
                     const int row = k * RPI + r_sub;  // lane `row` holds the source of row `row` (face m0 + row / 8, element row % 8)
-                    const int cr = __shfl_sync(0xffffffffu, code, row & 31);
                     if (lane_copies && row < nrow)
                     {
-                        const unsigned char *src = ub + (size_t)(cr < 0 ? 0 : cr) * (NP * 8);
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vb + (uint32_t)(k * RPI * NS * 8)), "l"(src), "r"(cr >= 0 ? 16u : 0u) : "memory");
+                        const unsigned char *src = ub + (size_t)(cr[k] < 0 ? 0 : cr[k]) * (NP * 8);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vb + (uint32_t)(k * RPI * NS * 8)), "l"(src), "r"(cr[k] >= 0 ? 16u : 0u) : "memory");
                     }
                 }
             }
             cp_async_arrive(full + slot);
             PBTE_STAMP(i, 6);
+            }
         }
     }
     else
@@ -1373,9 +1587,11 @@ __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_
                 }
             };
             PBTE_STAMP(i0, 9);
-            block(0, true, op);  // source / pseudo-time term: X = c1 T_old + c2 u_old (vectors 0 and 1 of the slot)
+            // source / pseudo-time term: X = c1 T_old + c2 u_old, formed here from vectors 0 and 1 of the slot or (march_xsrc) by the producer
+            constexpr int kFaceVec = march_xsrc(N) ? 1 : 2;
+            block(0, !march_xsrc(N), op);
             for (int m = 0; m < nin; ++m)
-                if (interior >> m & 1u) block((size_t)(2 + m) * kTile * NS, false, op + (size_t)(1 + m) * OPS);
+                if (interior >> m & 1u) block((size_t)(kFaceVec + m) * kTile * NS, false, op + (size_t)(1 + m) * OPS);
 #ifdef PBTE_TRACE
             if (acc[0][0][0] == 1.2345e300) PBTE_STAMP(i0, 15);  // the stamp below waits for the accumulators
 #endif

@@ -131,6 +131,28 @@ def test_c5_one_level_down_vs_oracle(variant, monkeypatch):
     hc.close()
 
 
+def test_c3_full_size_mesh_vs_oracle():
+    """The C3 MESH at its benchmark size (196 608 tetrahedra order 2: the 72 operator classes, list-scheduled tiles at their real fill)
+    with a quadrature the oracle finishes in seconds (2 x 4 directions, 2 bands): one iteration with the marching kernel."""
+    hc = pb.HostCase("unit-cube-tet", 2, 3, 3, 2, 4, True, False, BC3, num_spectral=1)
+    P = hc.problem
+    assert (P.ne, P.ndof, P.ndir, P.nband) == (196608, 10, 8, 2)
+    st, worst = stepwise_parity(P, 1, tol=parity_tolerance(P, "C3 full-size mesh"), kernel=3)
+    assert st.kernel_used == 3 and st.n_operator_classes == 72 and st.march_fill > 0.9
+    hc.close()
+
+
+def test_c5_full_size_mesh_vs_oracle():
+    """The C5 MESH at its benchmark size (65 536 quads order 4) with 8 azimuth points and 2 bands, consistent traces: two iterations
+    with the library's own kernel choice (the persistent marching kernel when there are more slots than resident CTAs, else the classic)."""
+    hc = pb.HostCase("unit-square-quad", 4, 5, 2, 1, 8, True, False, BC2, face_rule=1, num_spectral=1)
+    P = hc.problem
+    assert (P.ne, P.ndof, P.ndir, P.nband) == (65536, 25, 8, 2)
+    st, worst = stepwise_parity(P, 2, tol=parity_tolerance(P, "C5 full-size mesh, consistent traces"), kernel=0)
+    assert st.kernel_used == 3
+    hc.close()
+
+
 @pytest.mark.parametrize("peer", ["1", "0"])
 def test_two_devices_equal_one_device(c2_consistent, peer, monkeypatch):
     """Two handles on two GPUs of one process, directions split in halves, the exchange done by the library — over NVLink peer memory
