@@ -801,7 +801,6 @@ __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_
             const int q = lane & 7;  // lanes 0-7 hold the elements of the u_old rows, lanes 8-15 the same elements for the T_old rows
             const int first = (warp - kConsumerWarps - gbase % kSrcWarps + kSrcWarps) % kSrcWarps;
             int e_next = first < ntile ? __ldg(desc0 + (size_t)first * rows * kTile + q) : -1;
-            int slot = (gbase + first) % R, it = (gbase + first) / R;  // carried along: R is a run-time value, a division per tile is not free
             // Experiment (off): the ring cannot run far ahead of the consumers (a slot per consumer warp), so the u_old rows of a tile come
             // from HBM at the moment its slot frees; pull the rows of the tile kPrefetchAhead tiles further on into L2 now (one 128-byte
             // line per lane: 8 rows x 2 lines).
@@ -811,9 +810,9 @@ __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_
             constexpr int kPrefetchAhead = PBTE_L2_PREFETCH;
             [[maybe_unused]] int e_pf = (kPrefetchAhead > 0 && first + kPrefetchAhead < ntile) ? __ldg(desc0 + (size_t)(first + kPrefetchAhead) * rows * kTile + q) : -1;
             [[maybe_unused]] const double xc1 = P.slot_c1[s], xc2 = P.slot_c2[s];
-            for (int j = first; j < ntile; j += kSrcWarps, slot += kSrcWarps)
+            for (int j = first; j < ntile; j += kSrcWarps)
             {
-                if (slot >= R) slot -= R, ++it;
+                const int g = gbase + j, slot = g % R, it = g / R;
                 const int e = e_next;
                 const int32_t *desc_g = desc0 + (size_t)j * rows * kTile;
                 if (j + kSrcWarps < ntile) e_next = __ldg(desc_g + (size_t)kSrcWarps * rows * kTile + q);
@@ -836,18 +835,15 @@ __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_
                 unsigned char *sl = ring + (size_t)slot * slot_bytes;
                 PBTE_STAMP(t0 + j, 7);
                 const uint32_t vb = smem_u32(sl + hdr_bytes) + lane_off;
-                // all shuffles first, then all copies: a copy that waits for its own shuffle runs at the shuffle latency
-                int er[ITS];
-#pragma unroll
-                for (int k = 0; k < ITS; ++k) er[k] = __shfl_sync(0xffffffffu, e, (k * RPI + r_sub) & 7);
 #pragma unroll
                 for (int k = 0; k < ITS; ++k)
                 {
                     const int row = k * RPI + r_sub;  // rows 0-7 u_old, 8-15 T_old of the tile's elements
+                    const int er = __shfl_sync(0xffffffffu, e, row & 7);
                     if (lane_copies && row < 16)
                     {
-                        const unsigned char *src = (row < 8 ? ub : tb) + (size_t)(er[k] < 0 ? 0 : er[k]) * (NP * 8);
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vb + (uint32_t)(k * RPI * NS * 8)), "l"(src), "r"(er[k] >= 0 ? 16u : 0u) : "memory");
+                        const unsigned char *src = (row < 8 ? ub : tb) + (size_t)(er < 0 ? 0 : er) * (NP * 8);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vb + (uint32_t)(k * RPI * NS * 8)), "l"(src), "r"(er >= 0 ? 16u : 0u) : "memory");
                     }
                 }
                 if (lane < rows * 2) cp_async16(sl + lane * 16, reinterpret_cast<const unsigned char *>(desc_g) + lane * 16, 16u);
@@ -872,12 +868,11 @@ __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_
             int wm = t0;  // watermark: tiles [0, wm) of this slot are known to be stored
             const int first = (warp - kConsumerWarps - kSrcWarps - gbase % kNbrWarps + kNbrWarps) % kNbrWarps;
             const int32_t *d0 = desc0 + (size_t)first * rows * kTile;
-            int slot = (gbase + first) % R, it = (gbase + first) / R;
             int o_next = first < ntile ? __ldg(d0 + (1 + F) * kTile) : 0, L_next = first < ntile ? __ldg(d0 + (1 + F) * kTile + 3) : -1;
             int code_next = first < ntile ? __ldg(d0 + (1 + mq) * kTile + q) : -1;  // rows 1..4 always exist (rows = 2 + F, F >= 3)
-            for (int j = first; j < ntile; j += kNbrWarps, slot += kNbrWarps)
+            for (int j = first; j < ntile; j += kNbrWarps)
             {
-                if (slot >= R) slot -= R, ++it;
+                const int g = gbase + j, slot = g % R, it = g / R;
                 const int o = o_next, dep = L_next, code0 = code_next;
                 const int32_t *desc_g = desc0 + (size_t)j * rows * kTile;
                 if (j + kNbrWarps < ntile)
@@ -921,17 +916,16 @@ __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_
                     const int code = m0 == 0 ? code0 : ((m0 + mq < nin) ? __ldg(desc_g + (1 + m0 + mq) * kTile + q) : kSrcSkipCode);
                     const int nrow = min(nin - m0, 4) * kTile;
                     const uint32_t vb = smem_u32(sl + hdr_bytes) + (uint32_t)(((march_xsrc(N) ? 1 : 2) + m0) * kTile * NS * 8) + lane_off;
-                    int cr[ITN];
-#pragma unroll
-                    for (int k = 0; k < ITN; ++k) cr[k] = __shfl_sync(0xffffffffu, code, (k * RPI + r_sub) & 31);
 #pragma unroll
                     for (int k = 0; k < ITN; ++k)
                     {
+                        if (k * RPI >= nrow) break;
                         const int row = k * RPI + r_sub;  // lane `row` holds the source of row `row` (face m0 + row / 8, element row % 8)
+                        const int cr = __shfl_sync(0xffffffffu, code, row & 31);
                         if (lane_copies && row < nrow)
                         {
-                            const unsigned char *src = ub + (size_t)(cr[k] < 0 ? 0 : cr[k]) * (NP * 8);
-                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vb + (uint32_t)(k * RPI * NS * 8)), "l"(src), "r"(cr[k] >= 0 ? 16u : 0u) : "memory");
+                            const unsigned char *src = ub + (size_t)(cr < 0 ? 0 : cr) * (NP * 8);
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vb + (uint32_t)(k * RPI * NS * 8)), "l"(src), "r"(cr >= 0 ? 16u : 0u) : "memory");
                         }
                     }
                 }
@@ -1343,11 +1337,10 @@ __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_
         const int q = lane & 7;  // lanes 0-7 hold the elements of the u_old rows, lanes 8-15 the same elements for the T_old rows
         const int first = warp - kConsumerWarps;
         int e_next = first < NT ? __ldg(S.tile_desc + (size_t)(tbase + first) * rows * kTile + q) : -1;
-        int slot = first % R, it = first / R;  // carried along: R is a run-time value, a division per tile is not free
         [[maybe_unused]] const double xc1 = P.slot_c1[s], xc2 = P.slot_c2[s];
-        for (int i = first; i < NT; i += kSrcWarps, slot += kSrcWarps)
+        for (int i = first; i < NT; i += kSrcWarps)
         {
-            if (slot >= R) slot -= R, ++it;
+            const int slot = i % R, it = i / R;
             const int e = e_next;
             const int32_t *desc_g = S.tile_desc + (size_t)(tbase + i) * rows * kTile;
             if (i + kSrcWarps < NT) e_next = __ldg(desc_g + (size_t)kSrcWarps * rows * kTile + q);
@@ -1363,18 +1356,15 @@ __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_
             unsigned char *sl = ring + (size_t)slot * slot_bytes;
             PBTE_STAMP(i, 7);
             const uint32_t vb = smem_u32(sl + hdr_bytes) + lane_off;
-            // all shuffles first, then all copies: a copy that waits for its own shuffle runs at the shuffle latency
-            int er[ITS];
-#pragma unroll
-            for (int k = 0; k < ITS; ++k) er[k] = __shfl_sync(0xffffffffu, e, (k * RPI + r_sub) & 7);
 #pragma unroll
             for (int k = 0; k < ITS; ++k)
             {
                 const int row = k * RPI + r_sub;  // rows 0-7 u_old, 8-15 T_old of the tile's elements
+                const int er = __shfl_sync(0xffffffffu, e, row & 7);
                 if (lane_copies && row < 16)
                 {
-                    const unsigned char *src = (row < 8 ? ub : tb) + (size_t)(er[k] < 0 ? 0 : er[k]) * (NP * 8);
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vb + (uint32_t)(k * RPI * NS * 8)), "l"(src), "r"(er[k] >= 0 ? 16u : 0u) : "memory");
+                    const unsigned char *src = (row < 8 ? ub : tb) + (size_t)(er < 0 ? 0 : er) * (NP * 8);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vb + (uint32_t)(k * RPI * NS * 8)), "l"(src), "r"(er >= 0 ? 16u : 0u) : "memory");
                 }
             }
             if (lane < rows * 2) cp_async16(sl + lane * 16, reinterpret_cast<const unsigned char *>(desc_g) + lane * 16, 16u);
@@ -1399,12 +1389,11 @@ __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_
         int wm = 0;  // watermark: tiles [0, wm) of this class are known to be stored
         const int first = warp - kConsumerWarps - kSrcWarps;
         const int32_t *d0 = S.tile_desc + (size_t)(tbase + first) * rows * kTile;
-        int slot = first % R, it = first / R;
         int o_next = first < NT ? __ldg(d0 + (1 + F) * kTile) : 0, L_next = first < NT ? __ldg(d0 + (1 + F) * kTile + 3) : -1;
         int code_next = first < NT ? __ldg(d0 + (1 + mq) * kTile + q) : -1;  // rows 1..4 always exist (rows = 2 + F, F >= 3)
-        for (int i = first; i < NT; i += kNbrWarps, slot += kNbrWarps)
+        for (int i = first; i < NT; i += kNbrWarps)
         {
-            if (slot >= R) slot -= R, ++it;
+            const int slot = i % R, it = i / R;
             const int o = o_next, dep = L_next, code0 = code_next;
             const int32_t *desc_g = S.tile_desc + (size_t)(tbase + i) * rows * kTile;
             if (i + kNbrWarps < NT)
@@ -1446,17 +1435,16 @@ __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_
                 const int code = m0 == 0 ? code0 : ((m0 + mq < nin) ? __ldg(desc_g + (1 + m0 + mq) * kTile + q) : kSrcSkipCode);
                 const int nrow = min(nin - m0, 4) * kTile;
                 const uint32_t vb = smem_u32(sl + hdr_bytes) + (uint32_t)(((march_xsrc(N) ? 1 : 2) + m0) * kTile * NS * 8) + lane_off;
-                int cr[ITN];
-#pragma unroll
-                for (int k = 0; k < ITN; ++k) cr[k] = __shfl_sync(0xffffffffu, code, (k * RPI + r_sub) & 31);
 #pragma unroll
                 for (int k = 0; k < ITN; ++k)
                 {
+                    if (k * RPI >= nrow) break;
                     const int row = k * RPI + r_sub;  // lane `row` holds the source of row `row` (face m0 + row / 8, element row % 8)
+                    const int cr = __shfl_sync(0xffffffffu, code, row & 31);
                     if (lane_copies && row < nrow)
                     {
-                        const unsigned char *src = ub + (size_t)(cr[k] < 0 ? 0 : cr[k]) * (NP * 8);
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vb + (uint32_t)(k * RPI * NS * 8)), "l"(src), "r"(cr[k] >= 0 ? 16u : 0u) : "memory");
+                        const unsigned char *src = ub + (size_t)(cr < 0 ? 0 : cr) * (NP * 8);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vb + (uint32_t)(k * RPI * NS * 8)), "l"(src), "r"(cr >= 0 ? 16u : 0u) : "memory");
                     }
                 }
             }
