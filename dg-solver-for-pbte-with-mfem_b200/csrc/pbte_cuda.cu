@@ -175,6 +175,8 @@ struct pbte_handle
     // exchange of the temperature partial sums over NVLink peer memory (csrc/tail.cuh): this rank's buffer, the peers' buffers as
     // mapped into this process, the epoch counter
     bool peer_mode = false;
+    bool peer_fused = true;        // marching path: publish, wait, sum and finish inside the one tail launch (PBTE_PEER_FUSED=0: two launches)
+    bool sweep_finished = false;   // set by enqueue_sweep: the tail it enqueued has done the exchange and the finish step
     DevBuf<double> xchg;
     DevBuf<long long> xchg_epoch;
     DevBuf<const double *> d_peers;
@@ -653,6 +655,7 @@ DevTail make_tail(pbte_handle *h, int nparts, int per, bool finish)
     Z.peer = 0;
     Z.nranks = h->comm_size;
     Z.rank = h->comm_rank;
+    Z.qpart = h->mom_part.p;
     Z.xchg = h->xchg.p;
     Z.peers = h->d_peers.p;
     Z.epoch = h->xchg_epoch.p;
@@ -703,6 +706,7 @@ int enqueue_sweep(pbte_handle *h, int piv, bool fuse, int64_t *launch_count, boo
 {
     const DevProblem P = make_dev_problem(h);
     int64_t launches = 0;
+    h->sweep_finished = false;
     if (h->nslots() == 0 || h->max_levels == 0)
     {
         // a rank without directions contributes zeros
@@ -775,8 +779,17 @@ int enqueue_sweep(pbte_handle *h, int piv, bool fuse, int64_t *launch_count, boo
         }
         // [Tc | Qc] by one streaming pass over the flux; its last CTAs finish the iteration when `fuse`
         const int chunks = h->tail_chunks, per = (h->nslots() + chunks - 1) / chunks;
-        DevTail Z = make_tail(h, chunks, per, fuse);
-        if (peer) Z.peer = 1;
+        DevTail Z = make_tail(h, chunks, per, fuse || (peer && h->peer_fused));
+        if (peer && h->peer_fused)
+        {
+            // the whole multi-GPU iteration tail in this launch: temperature moment exchanged and finished, heat-flux partial sums
+            // left in mom_part for the read-out (complete_moments)
+            Z.peer = 3;
+            Z.m_end = 1;
+            h->sweep_finished = true;
+            h->qc_pending = true;
+        }
+        else if (peer) Z.peer = 1;
         iteration_tail_kernel<true><<<dim3((unsigned)h->tail_blocks, (unsigned)chunks), kTailThreads, 0, h->stream>>>(P, Z);
         CK(cudaGetLastError());
         if (launch_count) *launch_count = 2;
@@ -1854,6 +1867,8 @@ int graph_sweep(pbte_handle *h, int mode)
         if (h->peer_mode)
         {
             // the finish step reads the peers' temperature partial sums over NVLink itself: no collective call between the kernels
+            // (marching path: the tail launch has done that already)
+            if (h->sweep_finished) return PBTE_OK;
             if ((rc = enqueue_finish(h, true, true))) return rc;
             ++launches;
             return PBTE_OK;
@@ -2170,7 +2185,9 @@ int pbte_cuda_comm_get_unique_id(void *id)
 static int alloc_exchange(pbte_handle *h)
 {
     const size_t xrow = (size_t)h->ne * h->np;
-    CK(h->xchg.alloc(2 * xrow + 16));
+    const int epb = kTailThreads / (h->np / 2), blocks = (h->ne + epb - 1) / epb;  // one flag per element block of the tail grid
+    if (const char *ev = std::getenv("PBTE_PEER_FUSED")) h->peer_fused = std::atoi(ev) != 0;
+    CK(h->xchg.alloc(2 * xrow + kXchgFlag0 + (size_t)blocks + 16));
     CK(cudaMemsetAsync(h->xchg.p, 0, h->xchg.count * sizeof(double), h->stream));
     CK(h->xchg_epoch.alloc(1));
     CK(cudaMemsetAsync(h->xchg_epoch.p, 0, sizeof(long long), h->stream));

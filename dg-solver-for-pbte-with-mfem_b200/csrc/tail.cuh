@@ -43,17 +43,26 @@ struct DevTail
     double *block_part;    // [gridDim.x][3]
     DevCtrl *ctrl;
     double *hist;          // device view of the pinned history ring [kHistRing][4]
-    // Multi-GPU exchange over NVLink peer memory (instead of an NCCL all-reduce between the two kernels):
-    //   peer = 1 (tail of a sweep): the temperature partial sums go into this rank's exchange buffer xchg[parity][ne][np]; the last
-    //            CTA publishes epoch + 1 in the flag behind it (release at system scope);
-    //   peer = 2 (finish): waits until every peer has published epoch + 1, adds the N partial buffers in rank order straight from the
-    //            peers' memory (P2P loads, identical order on every rank: identical sums), and finishes the iteration.
-    // The buffers alternate with the parity of the epoch, so a rank one iteration ahead never overwrites what a peer still reads.
+    // Multi-GPU exchange over NVLink peer memory (instead of an NCCL all-reduce between the two kernels).  Every element block of the
+    // tail grid has its own flag, so the exchange of a block starts when that block is ready on every rank, not when the slowest
+    // block of the slowest rank is:
+    //   peer = 1 (publish): the block's temperature partial sums go into this rank's exchange buffer xchg[parity][ne][np]; the CTA
+    //            then stores epoch + 1 into the block's flag (release at system scope);
+    //   peer = 2 (finish): waits until every peer has published epoch + 1 for the block, adds the N partial rows in rank order straight
+    //            from the peers' memory (P2P loads, identical order on every rank: identical sums), and finishes the iteration;
+    //   peer = 3 (marching path: publish, wait, sum and finish in the ONE streaming tail launch): a CTA publishes before it waits and
+    //            CTAs start in block order on every rank, so whatever a waiting CTA waits for was started earlier on the peer and
+    //            does not wait itself before publishing: no deadlock even when the grid is larger than what is resident.
+    // The buffers alternate with the parity of the epoch: a rank can start iteration k + 1 only after every peer has published every
+    // block of iteration k, i.e. after every peer is done reading iteration k - 1, whose buffer iteration k + 1 overwrites.
     int peer, nranks, rank;
-    double *xchg;                   // this rank's buffer: 2 * ne * np doubles, then the flag (long long)
+    double *qpart;                  // peer = 3: where the heat-flux partial sums of this rank go (all-reduced once, at the read-out)
+    double *xchg;                   // this rank's buffer: 2 * ne * np doubles, then kXchgFlag0 + number of element blocks flags (long long)
     const double *const *peers;     // [nranks] every rank's buffer as mapped here (cudaIpcOpenMemHandle / peer access)
     long long *epoch;               // iterations exchanged so far (device counter, never reset; advanced by the finish step)
 };
+
+constexpr int kXchgFlag0 = 2;  // first per-block flag, in 8-byte units behind the two buffers
 
 __device__ __forceinline__ long long ld_acquire_sys(const long long *p)
 {
@@ -162,28 +171,41 @@ __global__ void __launch_bounds__(kTailThreads, PBTE_TAIL_MINBLOCKS) iteration_t
     // ---- multi-GPU: wait for the peers' partial sums of this iteration ------------------------------------------------------------
     const size_t xrow = (size_t)ne * np;  // doubles per exchange buffer
     long long ep = 0;
+    auto wait_for_peers = [&]() {
+        if (t < Z.nranks && t != Z.rank)
+        {
+            const long long *flag = reinterpret_cast<const long long *>(Z.peers[t] + 2 * xrow) + kXchgFlag0 + blockIdx.x;
+            const long long t0 = clock64();
+            while (ld_acquire_sys(flag) < ep + 1)
+            {
+                __nanosleep(100);
+                if (clock64() - t0 > 20000000000LL)
+                {
+                    // a peer that never arrives (its process died): give up loudly instead of hanging the GPU
+                    atomicCAS(P.error_flag, 0, PBTE_ERR_CUDA);
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+    };
+    // the N ranks' partial sums of this thread's chunk in rank order, straight from their memory (uncached: the buffers are rewritten
+    // every other iteration)
+    auto sum_over_ranks = [&](double &a, double &b) {
+        const size_t off = (size_t)(ep & 1) * xrow + (size_t)e * np + i0;
+        a = 0.0;
+        b = 0.0;
+        for (int rk = 0; rk < Z.nranks; ++rk)
+        {
+            const double2 w = __ldcv(reinterpret_cast<const double2 *>(Z.peers[rk] + off));
+            a += w.x;
+            b += w.y;
+        }
+    };
     if (Z.peer)
     {
         ep = *Z.epoch;
-        if (Z.peer == 2)
-        {
-            if (t < Z.nranks && t != Z.rank)
-            {
-                const long long *flag = reinterpret_cast<const long long *>(Z.peers[t] + 2 * xrow);
-                const long long t0 = clock64();
-                while (ld_acquire_sys(flag) < ep + 1)
-                {
-                    __nanosleep(200);
-                    if (clock64() - t0 > 20000000000LL)
-                    {
-                        // a peer that never arrives (its process died): give up loudly instead of hanging the GPU
-                        atomicCAS(P.error_flag, 0, PBTE_ERR_CUDA);
-                        break;
-                    }
-                }
-            }
-            __syncthreads();
-        }
+        if (Z.peer == 2) wait_for_peers();
     }
     // ---- sum of the partial vectors, ascending (fixed order) ---------------------------------------------------------------
     if (valid)
@@ -199,15 +221,8 @@ __global__ void __launch_bounds__(kTailThreads, PBTE_TAIL_MINBLOCKS) iteration_t
                 double a = 0.0, b = 0.0;
                 if (nparts == 0 && Z.peer == 2 && m == 0)
                 {
-                    // the N ranks' partial sums in rank order, straight from their memory (uncached: the buffers are rewritten every
-                    // other iteration); the all-reduced row also goes to the local moment vector
-                    const size_t off = (size_t)(ep & 1) * xrow + (size_t)e * np + i0;
-                    for (int rk = 0; rk < Z.nranks; ++rk)
-                    {
-                        const double2 w = __ldcv(reinterpret_cast<const double2 *>(Z.peers[rk] + off));
-                        a += w.x;
-                        b += w.y;
-                    }
+                    // the all-reduced row also goes to the local moment vector
+                    sum_over_ranks(a, b);
                     Z.mom[x0] = a;
                     if (has1) Z.mom[x0 + 1] = b;
                 }
@@ -231,29 +246,38 @@ __global__ void __launch_bounds__(kTailThreads, PBTE_TAIL_MINBLOCKS) iteration_t
             for (int m = 0; m <= kMaxDim; ++m)
             {
                 if (m >= nm) break;
-                if (m == 0 && Z.peer == 1)
+                if (m == 0 && (Z.peer == 1 || Z.peer == 3))
                 {
                     // temperature partial sums of this rank: into the exchange buffer the peers read (padded rows: 16-byte stores)
                     *reinterpret_cast<double2 *>(Z.xchg + (size_t)(ep & 1) * xrow + (size_t)e * np + i0) = make_double2(v[0][0], has1 ? v[0][1] : 0.0);
                     continue;
                 }
-                Z.mom[(size_t)m * block + x0] = v[m][0];
-                if (has1) Z.mom[(size_t)m * block + x0 + 1] = v[m][1];
+                double *dst = Z.peer == 3 ? Z.qpart : Z.mom;
+                dst[(size_t)m * block + x0] = v[m][0];
+                if (has1) dst[(size_t)m * block + x0 + 1] = v[m][1];
             }
     }
-    if (!Z.finish)
+    if (Z.peer == 1 || Z.peer == 3)
     {
-        if (Z.peer == 1)
+        // publish the block: every thread's rows are written (CTA barrier), then one release at system scope
+        __syncthreads();
+        if (t == 0)
         {
-            // publish: the last CTA of the grid (every CTA that reaches this point has written its rows) releases the flag
-            if (last_arrival(Z.tickets + gridDim.x, gridDim.x, &s_flag) && t == 0)
-            {
-                __threadfence_system();
-                st_release_sys(reinterpret_cast<long long *>(Z.xchg + 2 * xrow), ep + 1);
-            }
+            __threadfence_system();
+            st_release_sys(reinterpret_cast<long long *>(Z.xchg + 2 * xrow) + kXchgFlag0 + blockIdx.x, ep + 1);
         }
-        return;
     }
+    if (Z.peer == 3)
+    {
+        wait_for_peers();
+        if (valid)
+        {
+            sum_over_ranks(v[0][0], v[0][1]);
+            Z.mom[x0] = v[0][0];
+            if (has1) Z.mom[x0 + 1] = v[0][1];
+        }
+    }
+    if (!Z.finish) return;
 
     // ---- finish: cell integrals, norms, hand-over ----------------------------------------------------------------------------
     const int mb = Z.m_begin, me = min(Z.m_end, nm);
@@ -350,7 +374,7 @@ __global__ void __launch_bounds__(kTailThreads, PBTE_TAIL_MINBLOCKS) iteration_t
         h[2] = tot[2];
         h[3] = (double)*P.error_flag;
         c->iter = it + 1;
-        if (Z.peer == 2) *Z.epoch = ep + 1;
+        if (Z.peer >= 2) *Z.epoch = ep + 1;
         // the reference's stop test: res = ||Tv - Tv_prev|| / ||Tv|| < tol (src/PBTESolver.cpp:327)
         if (tot[1] > 0.0 && sqrt(tot[0]) / sqrt(tot[1]) < c->tol) c->stop = 1;
         __threadfence_system();

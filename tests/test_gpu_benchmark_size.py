@@ -153,14 +153,15 @@ def test_c5_full_size_mesh_vs_oracle():
     hc.close()
 
 
-@pytest.mark.parametrize("peer", ["1", "0"])
-def test_two_devices_equal_one_device(c2_consistent, peer, monkeypatch):
+@pytest.mark.parametrize("peer,fused", [("1", "1"), ("1", "0"), ("0", "1")])
+def test_two_devices_equal_one_device(c2_consistent, peer, fused, monkeypatch):
     """Two handles on two GPUs of one process, directions split in halves, the exchange done by the library — over NVLink peer memory
-    inside the finish kernel (peer = 1, the default) or as an NCCL all-reduce (PBTE_PEER_ALLREDUCE=0): same iterates as one handle on
-    one GPU (the sum order of the moments differs: 1e-13)."""
+    inside the one tail launch of an iteration (the default), in a finish kernel of its own (PBTE_PEER_FUSED=0), or as an NCCL
+    all-reduce (PBTE_PEER_ALLREDUCE=0): same iterates as one handle on one GPU (the sum order of the moments differs: 1e-13)."""
     if pb.device_count() < 2:
         pytest.skip("needs two CUDA devices")
     monkeypatch.setenv("PBTE_PEER_ALLREDUCE", peer)
+    monkeypatch.setenv("PBTE_PEER_FUSED", fused)
     P = c2_consistent.problem  # well-conditioned local systems: the two summation orders agree to rounding
     one = pb.Solver(P, device=0)
     one.build_schedule()
