@@ -186,6 +186,7 @@ struct pbte_handle
     // [2] sweep + NCCL all-reduce + finish (whole multi-GPU iteration of this rank)
     cudaGraphExec_t graph_exec[3] = {nullptr, nullptr, nullptr};
     int graph_mode[3] = {-1, -1, -1};
+    bool graph_failed[3] = {false, false, false};  // capture or instantiation of this kind of graph failed once: plain launches from then on
     bool nccl_in_graph = true;
 
     // stats
@@ -1857,7 +1858,7 @@ int graph_sweep(pbte_handle *h, int mode)
     if (h->pivots.p) piv = h->pivots_recorded ? 2 : 1;
     CK(cudaEventRecord(h->ev0, h->stream));
     int64_t launches = 0;
-    bool graph_ok = h->use_graph && piv != 1 && h->max_levels > 0;
+    bool graph_ok = h->use_graph && piv != 1 && h->max_levels > 0 && !h->graph_failed[mode];
 #ifdef PBTE_TRACE
     if (std::getenv("PBTE_TRACE_FILE")) graph_ok = false;  // the traced sweep synchronises and writes a file
 #endif
@@ -1903,10 +1904,12 @@ int graph_sweep(pbte_handle *h, int mode)
             // capture or instantiation failed: this handle goes on with plain launches (a graph with an NCCL node: without NCCL in it)
             (void)cudaGetLastError();
             h->graph_exec[g] = nullptr;
+            h->graph_failed[g] = true;
             if (mode == 2) h->nccl_in_graph = false;
             else h->use_graph = 0;
             graph_ok = false;
-            if (mode == 2) return enqueue_iteration(h);
+            // NCCL form: sweep graph, all-reduce and finish as separate enqueues; peer form: the same kernels as plain launches below
+            if (mode == 2 && !h->peer_mode) return enqueue_iteration(h);
         }
         else
         {
