@@ -422,6 +422,27 @@ __device__ __forceinline__ void cp_async16(void *dst, const void *src, uint32_t 
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
 }
+// L2 eviction hints (experiment, PBTE_L2_HINTS): the u_old rows of a sweep are read once (evict first), the rows a sweep stores are
+// read again by the downwind tiles, by the iteration tail and by the next sweep (evict last)
+#ifndef PBTE_L2_HINTS
+#define PBTE_L2_HINTS 0  // bit 0: evict-first loads of u_old, bit 1: evict-last stores of the new flux
+#endif
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void st_global_f64x2_hint(double *dst, double2 v, uint64_t policy)
+{
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(dst), "d"(v.x), "d"(v.y), "l"(policy) : "memory");
+}
 // the barrier receives one arrival from this thread once all its earlier cp.async have landed
 __device__ __forceinline__ void cp_async_arrive(uint64_t *bar)
 {
@@ -1336,6 +1357,7 @@ __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_
         const unsigned char *ub = reinterpret_cast<const unsigned char *>(u) + lch * 16, *tb = reinterpret_cast<const unsigned char *>(P.tc_prev) + lch * 16;
         const int q = lane & 7;  // lanes 0-7 hold the elements of the u_old rows, lanes 8-15 the same elements for the T_old rows
         const int first = warp - kConsumerWarps;
+        [[maybe_unused]] const uint64_t pol_first = PBTE_L2_HINTS ? l2_policy_evict_first() : 0;
         int e_next = first < NT ? __ldg(S.tile_desc + (size_t)(tbase + first) * rows * kTile + q) : -1;
         [[maybe_unused]] const double xc1 = P.slot_c1[s], xc2 = P.slot_c2[s];
         for (int i = first; i < NT; i += kSrcWarps)
@@ -1364,7 +1386,12 @@ __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_
                 if (lane_copies && row < 16)
                 {
                     const unsigned char *src = (row < 8 ? ub : tb) + (size_t)(er < 0 ? 0 : er) * (NP * 8);
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vb + (uint32_t)(k * RPI * NS * 8)), "l"(src), "r"(er >= 0 ? 16u : 0u) : "memory");
+                    if ((PBTE_L2_HINTS & 1) && row < 8)
+                        asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(vb + (uint32_t)(k * RPI * NS * 8)), "l"(src),
+                                     "r"(er >= 0 ? 16u : 0u), "l"(pol_first)
+                                     : "memory");
+                    else
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vb + (uint32_t)(k * RPI * NS * 8)), "l"(src), "r"(er >= 0 ? 16u : 0u) : "memory");
                 }
             }
             if (lane < rows * 2) cp_async16(sl + lane * 16, reinterpret_cast<const unsigned char *>(desc_g) + lane * 16, 16u);
@@ -1459,6 +1486,7 @@ __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_
         const int q = lane >> 2, r = lane & 3;
         const double c1 = P.slot_c1[s], c2 = P.slot_c2[s];
         const double *oph = S.h_smem ? s_h : S.oph + (size_t)s * noc * F * N;
+        [[maybe_unused]] const uint64_t pol_last = PBTE_L2_HINTS ? l2_policy_evict_last() : 0;
         // One pass = T tiles (1 or 2) of one operator class whose ring slots are full: U_t = X_t P^T + sum_m Unbr_t,m Q_m^T.
         // One matrix block = KS k steps; per k step the B fragments of all MT row blocks (two per 16-byte load from the staged
         // operator) feed T * MT MMAs, the A fragments come from the staged vectors.  With T = 2 every operator fragment read from
@@ -1622,7 +1650,11 @@ __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_
                     {
                         // 16-byte stores; an odd ndof has one padding column per row, which stays zero
                         const int d0 = 8 * I + 2 * r;
-                        if (d0 < NP) *reinterpret_cast<double2 *>(dst + d0) = make_double2(acc[t][I][0], d0 + 1 < N ? acc[t][I][1] : 0.0);
+                        if (d0 < NP)
+                        {
+                            if (PBTE_L2_HINTS & 2) st_global_f64x2_hint(dst + d0, make_double2(acc[t][I][0], d0 + 1 < N ? acc[t][I][1] : 0.0), pol_last);
+                            else *reinterpret_cast<double2 *>(dst + d0) = make_double2(acc[t][I][0], d0 + 1 < N ? acc[t][I][1] : 0.0);
+                        }
                     }
                 }
             PBTE_STAMP(i0, 10);
