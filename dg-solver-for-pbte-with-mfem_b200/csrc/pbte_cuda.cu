@@ -107,6 +107,8 @@ struct pbte_handle
     std::vector<int> cls_slot_begin;       // [nclass+1] (in slots)
     std::vector<int32_t> h_pass, h_level;  // [nclass][ne]
     std::vector<int> level_offsets;        // [max_levels+1] into items
+    DevBuf<int32_t> item_done;             // [nclass][ne] "stored" flags of the whole-sweep launch of the per-element kernel
+    int warp_grid = 0;                     // its grid: what is resident at once (0: one launch per wavefront level)
     DevBuf<int2> items;
     DevBuf<int32_t> d_cls_slot_begin;
     DevBuf<uint8_t> cls_out, cls_in, pivots;
@@ -319,7 +321,7 @@ DevProblem make_dev_problem(pbte_handle *h)
 }
 
 // ---- warp-kernel dispatch ------------------------------------------------------------------------
-typedef void (*WarpKernelFn)(DevProblem, const int2 *, int, WarpKernelShape);
+typedef void (*WarpKernelFn)(DevProblem, const int2 *, int, int, int32_t *, WarpKernelShape);
 
 template <int N, int DIM>
 WarpKernelFn pick_piv(int piv)
@@ -800,13 +802,22 @@ int enqueue_sweep(pbte_handle *h, int piv, bool fuse, int64_t *launch_count, boo
     {
         WarpKernelFn fn = pick_warp_kernel(h->n, h->dim, piv);
         const size_t smem = sweep_warp_smem(h->n, h->dim, h->shape);
-        for (int L = 0; L < h->max_levels; ++L)
+        const int total = h->level_offsets[h->max_levels];
+        if (h->warp_grid > 0)
         {
-            const int begin = h->level_offsets[L], count = h->level_offsets[L + 1] - begin;
-            if (count == 0) continue;
-            fn<<<count, kWarpsPerCta * 32, smem, h->stream>>>(P, h->items.p, begin, h->shape);
+            // the whole sweep in one launch: resident CTAs walk the level-major item list, upwind neighbours tracked by flags
+            CK(cudaMemsetAsync(h->item_done.p, 0, h->item_done.count * sizeof(int32_t), h->stream));
+            fn<<<std::min(h->warp_grid, total), kWarpsPerCta * 32, smem, h->stream>>>(P, h->items.p, 0, total, h->item_done.p, h->shape);
             ++launches;
         }
+        else
+            for (int L = 0; L < h->max_levels; ++L)
+            {
+                const int begin = h->level_offsets[L], count = h->level_offsets[L + 1] - begin;
+                if (count == 0) continue;
+                fn<<<count, kWarpsPerCta * 32, smem, h->stream>>>(P, h->items.p, begin, count, nullptr, h->shape);
+                ++launches;
+            }
     }
     else
     {
@@ -1605,8 +1616,19 @@ int pbte_cuda_build_schedule(pbte_handle_t *h)
             CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
             if (smem <= (size_t)max_optin)
             {
+                int per_sm = 1 << 30, sms = 0;
                 for (int piv = 0; piv < 3; ++piv)
+                {
                     CK(cudaFuncSetAttribute(pick_warp_kernel(h->n, h->dim, piv), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    int occ = 0;
+                    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_warp_kernel(h->n, h->dim, piv), kWarpsPerCta * 32, smem));
+                    per_sm = std::min(per_sm, occ);
+                }
+                CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+                // one launch per sweep with as many CTAs as are resident at once (PBTE_WARP_PERSIST=0: one launch per wavefront level)
+                h->warp_grid = per_sm > 0 ? per_sm * sms : 0;
+                if (const char *ev = std::getenv("PBTE_WARP_PERSIST"))
+                    if (std::atoi(ev) == 0) h->warp_grid = 0;
                 h->kernel_used = 2;
             }
         }
@@ -1636,7 +1658,11 @@ int pbte_cuda_build_schedule(pbte_handle_t *h)
                 else h->partial.release();
                 h->items.release();  // the level lists of (class, element) items drive the per-element kernels only
             }
-            else CK(h->partial.alloc((size_t)nclass * vec));
+            else
+            {
+                CK(h->partial.alloc((size_t)nclass * vec));
+                if (h->kernel_used == 2 && h->warp_grid > 0) CK(h->item_done.alloc((size_t)nclass * ne));
+            }
         }
         h->pivots.release();
         h->pivots_recorded = false;

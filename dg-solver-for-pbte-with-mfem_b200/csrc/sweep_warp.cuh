@@ -27,9 +27,19 @@ struct WarpKernelShape
 };
 
 // PIV: 0 = search pivots, 1 = search and record, 2 = replay recorded pivots
+// Two ways to launch it:
+//   one launch per wavefront level   grid = items of the level, item_count = grid size, done = nullptr;
+//   ONE launch for the whole sweep   grid = resident CTAs, item_count = all items (level-major), done = [nclass][ne] flags zeroed before
+//                                    the launch: a CTA takes the items blockIdx.x, + gridDim.x, ... in order, waits until the upwind
+//                                    neighbours of its item are flagged (acquire at GPU scope), and flags its own item after the
+//                                    flux is stored (release).  An item waits only for items earlier in the list, every CTA is
+//                                    resident and works in order: no deadlock, no launch per level, no idle tail per level.
 template <int N, int DIM, int PIV>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) sweep_warp_kernel(DevProblem P, const int2 *__restrict__ items, int item_begin,
-                                                                      WarpKernelShape shape)
+#ifndef PBTE_WARP_MINBLOCKS
+#define PBTE_WARP_MINBLOCKS 1  // experiment: ask for more CTAs per SM (fewer registers per thread)
+#endif
+__global__ void __launch_bounds__(kWarpsPerCta * 32, PBTE_WARP_MINBLOCKS) sweep_warp_kernel(DevProblem P, const int2 *__restrict__ items, int item_begin, int item_count,
+                                                                      int32_t *done, WarpKernelShape shape)
 {
     constexpr int NN = N * N;
     constexpr unsigned FULL = 0xffffffffu;
@@ -37,7 +47,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sweep_warp_kernel(DevProble
     if (*P.stop) return;  // the iteration before this one met the stop test (csrc/tail.cuh)
     const int F = P.F;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int2 it = items[item_begin + blockIdx.x];
+    bool singular = false;
+    for (int item = blockIdx.x; item < item_count; item += gridDim.x)
+    {
+    const int2 it = items[item_begin + item];
     const int c = it.x, e = it.y;
     const int s0 = P.cls_slot_begin[c], s1 = P.cls_slot_begin[c + 1];
     const int ndir_c = (s1 - s0) / P.nband;
@@ -63,6 +76,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sweep_warp_kernel(DevProble
         {
             s_fslot[f] = (f < F && (outm >> f & 1u)) ? (signed char)nf++ : (signed char)-1;
             s_kslot[f] = (f < F && (inm >> f & 1u)) ? (signed char)nk++ : (signed char)-1;
+        }
+    }
+    if (done && threadIdx.x < F && (inm >> threadIdx.x & 1u))
+    {
+        // whole-sweep launch: the upwind neighbours of this item must be stored (their CTAs flagged them with a release)
+        const int nb = P.fnbr[(size_t)e * F + threadIdx.x];
+        if (nb >= 0)
+        {
+            const int32_t *flag = done + (size_t)c * P.ne + nb;
+            int v;
+            do
+            {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+                if (!v) __nanosleep(100);
+            } while (!v);
         }
     }
     __syncthreads();
@@ -99,7 +127,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sweep_warp_kernel(DevProble
     const int row = active ? lane : 0;  // idle lanes shadow row 0 (their results are discarded)
     const double T_old = P.tc_prev[(size_t)e * P.np + row];
     double accT = 0.0, accQ[kMaxDim] = {0.0, 0.0, 0.0};
-    bool singular = false;
 
     for (int kd = warp; kd < ndir_c; kd += kWarpsPerCta)
     {
@@ -145,7 +172,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sweep_warp_kernel(DevProble
                 if (f < F && af[f] < 0.0)
                 {
                     const int nb = P.fnbr[(size_t)e * F + f];
-                    if (nb >= 0 && active) vec[(1 + f) * N + lane] = P.flux[((size_t)s * P.ne + nb) * P.np + lane];
+                    if (nb >= 0 && active) vec[(1 + f) * N + lane] = __ldcg(P.flux + ((size_t)s * P.ne + nb) * P.np + lane);  // through L2: written by another SM during this launch
                 }
             }
             __syncwarp();
@@ -262,6 +289,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sweep_warp_kernel(DevProble
             P.partial[(((size_t)c * (1 + DIM) + m) * P.ne + e) * N + i] = sum;
         }
     }
+    // every warp's flux rows of this item are stored before the item is flagged (and before the next item reuses shared memory)
+    __syncthreads();
+    if (done && threadIdx.x == 0)
+    {
+        __threadfence();
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(done + (size_t)c * P.ne + e), "r"(1) : "memory");
+    }
+    }  // items of this CTA
     if (singular && lane == 0) atomicCAS(P.error_flag, 0, PBTE_ERR_SINGULAR);
 }
 

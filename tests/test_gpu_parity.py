@@ -362,6 +362,22 @@ def test_graph_replay_equals_plain_launches_and_is_reproducible():
     hc.close()
 
 
+@pytest.mark.parametrize("name,policy", [("tet_p2", 0), ("c2_hex_p2_small", 1), ("quad_p2", 0)])
+def test_per_element_kernel_whole_sweep_launch_equals_level_launches(name, policy, monkeypatch):
+    """Kernel 2 as ONE launch per sweep (resident CTAs walk the level-major item list, upwind neighbours tracked by release / acquire
+    flags) against one launch per wavefront level (PBTE_WARP_PERSIST=0): the same systems in a different order in time, identical bits."""
+    hc = host_case(name)
+    monkeypatch.setenv("PBTE_WARP_PERSIST", "0")
+    a = gpu_solve(hc.problem, 3, kernel=2, cache_policy=policy)
+    monkeypatch.setenv("PBTE_WARP_PERSIST", "1")
+    b = gpu_solve(hc.problem, 3, kernel=2, cache_policy=policy)
+    assert a["stats"].kernel_used == 2 and b["stats"].kernel_used == 2
+    assert b["stats"].kernel_launches < a["stats"].kernel_launches
+    for k in ("coeff", "Tc", "Qc", "Tv", "Qv"):
+        assert np.array_equal(a[k], b[k]), k
+    hc.close()
+
+
 def test_bulk_coefficient_transfer_equals_block_by_block():
     """pbte_cuda_upload_coeff_all / download_coeff_all (staged bulk transfers, repacking on the device) against the per-block calls."""
     hc = host_case("tet_p2")
