@@ -536,8 +536,9 @@ def run_gpu(args, rank, world, local_rank):
         fin = mean_interior_inflow_faces(P, k0, k1)
         fpu = flops_per_update_shared(P.ndof, fin)
         kname = ("sweep_march_regop_kernel" if st1.march_variant == 1 else
-                 ("sweep_march_kernel (persistent, work lists)" if st1.march_persistent else "sweep_march_classic_kernel (one CTA per slot)"))
-        kdesc = (f"{kname}<{P.ndof}> (one launch per step: marching CTAs walk the {nlev} wavefront levels of every (direction, band) slot,"
+                 ("sweep_march_kernel" if st1.march_persistent else "sweep_march_classic_kernel"))
+        khow = "persistent CTAs with work lists" if (st1.march_persistent and st1.march_variant != 1) else "one CTA per slot"
+        kdesc = (f"{kname}<{P.ndof}> ({khow}; one launch per step: marching CTAs walk the {nlev} wavefront levels of every (direction, band) slot,"
                  f" {st1.n_operator_classes} operator class(es), tile fill {st1.march_fill:.2f}), followed by iteration_tail_kernel; sweep + tail {sweep_s * 1e3:.3f} ms per step"
                  f" by CUDA events on the sweep stream; algorithmic flops = 2n(1+F_in)+2 = {fpu:.1f} per update with F_in = {fin:.3f} interior inflow"
                  f" faces per element (shared-operator algebra, DESIGN.md); the per-element LU algebra of the reference would be"
