@@ -183,6 +183,15 @@ def test_two_devices_equal_one_device(c2_consistent, peer, fused, monkeypatch):
             assert rel(got[k], want[k]) <= 1e-12, (k, rel(got[k], want[k]))
     k0, k1 = halves[1].dir_range
     assert rel(halves[1].download_coeff(k0, 1), one.download_coeff(k0, 1)) <= 1e-12  # a slot's flux sees the partition only through Tc
+    # the stop test: every device forms the same sums, so all of them stop at the iteration one device stops at
+    if hist1[2] < min(hist1[0], hist1[1]):
+        tol_stop = 0.5 * (hist1[2] + min(hist1[0], hist1[1]))
+        for s in halves:
+            s.reset_state()
+        it3, res3, hist3 = pb.solve_multi(halves, 10, tol_stop)
+        assert it3 == 3 and abs(res3 - hist1[2]) <= 1e-11 * hist1[2]
+        for s in halves:
+            assert rel(s.download_moments()["Tc"], halves[0].download_moments()["Tc"]) == 0.0  # identical on every device
     for s in halves:
         s.close()
     one.close()
