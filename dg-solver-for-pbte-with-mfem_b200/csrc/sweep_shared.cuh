@@ -1605,9 +1605,64 @@ __global__ void __launch_bounds__(march_threads(N), march_ctas_per_sm(N)) sweep_
             PBTE_STAMP(i0, 9);
             // source / pseudo-time term: X = c1 T_old + c2 u_old, formed here from vectors 0 and 1 of the slot or (march_xsrc) by the producer
             constexpr int kFaceVec = march_xsrc(N) ? 1 : 2;
+#ifndef PBTE_PIPE_B
+#define PBTE_PIPE_B 0
+#endif
+            // Experiment (off).  Operators read from global memory with few k steps (simplices): the B fragments of the NEXT matrix block
+            // are requested before the MMAs of the current one, so that a block does not start with an exposed L1 / L2 round trip (tile
+            // timeline of the C3 slice: 2000 cycles for 24 MMAs).  Same operands, same order of the MMAs: identical bits.  Measured
+            // (profiles/r02_kernel_probes.txt, run y): 3.07 against 2.74 ms on the C3 slice - at the 64 registers two CTAs of 16 warps
+            // leave a thread, the second fragment set spills and its copies cost more than the round trip.
+            constexpr bool kPipeB = PBTE_PIPE_B != 0 && !FRAG_B && T == 1 && KS <= 4;
+            if constexpr (kPipeB)
+            {
+                auto load_b = [&](const double *opb, double2(&bq)[KS][MP]) {
+#pragma unroll
+                    for (int k = 0; k < KS; ++k)
+#pragma unroll
+                        for (int Ip = 0; Ip < MP; ++Ip)
+                        {
+                            const int row = 16 * Ip + q, col = 4 * k + r;
+                            bq[k][Ip].x = (row < N && col < N) ? __ldg(opb + row * N + col) : 0.0;
+                            bq[k][Ip].y = (row + 8 < N && col < N) ? __ldg(opb + (row + 8) * N + col) : 0.0;
+                        }
+                };
+                auto mma_block = [&](size_t voff, bool source, const double2(&bq)[KS][MP]) {
+                    const double *va = vec[0] + voff;
+                    double xa[KS];
+#pragma unroll
+                    for (int k = 0; k < KS; ++k) xa[k] = source ? fma(c2, va[4 * k], c1 * va[(size_t)kTile * NS + 4 * k]) : va[4 * k];
+#pragma unroll
+                    for (int k = 0; k < KS; ++k)
+#pragma unroll
+                        for (int I = 0; I < MT; ++I) dmma_m8n8k4(acc[0][I][0], acc[0][I][1], xa[k], (I & 1) ? bq[k][I >> 1].y : bq[k][I >> 1].x);
+                };
+                double2 bcur[KS][MP], bnext[KS][MP];
+                load_b(op, bcur);
+                unsigned rest = interior & ((1u << nin) - 1u);  // interior inflow faces still to do, in ascending order
+                size_t voff = 0;
+                bool source = !march_xsrc(N);
+                while (true)
+                {
+                    const int mn = rest ? __ffs(rest) - 1 : -1;
+                    if (mn >= 0) load_b(op + (size_t)(1 + mn) * OPS, bnext);
+                    mma_block(voff, source, bcur);
+                    if (mn < 0) break;
+                    rest &= rest - 1;
+                    voff = (size_t)(kFaceVec + mn) * kTile * NS;
+                    source = false;
+#pragma unroll
+                    for (int k = 0; k < KS; ++k)
+#pragma unroll
+                        for (int Ip = 0; Ip < MP; ++Ip) bcur[k][Ip] = bnext[k][Ip];
+                }
+            }
+            else
+            {
             block(0, !march_xsrc(N), op);
             for (int m = 0; m < nin; ++m)
                 if (interior >> m & 1u) block((size_t)(kFaceVec + m) * kTile * NS, false, op + (size_t)(1 + m) * OPS);
+            }
 #ifdef PBTE_TRACE
             if (acc[0][0][0] == 1.2345e300) PBTE_STAMP(i0, 15);  // the stamp below waits for the accumulators
 #endif
