@@ -2408,6 +2408,8 @@ int pbte_cuda_comm_detach(pbte_handle_t *h)
     if (st) return st;
     DeviceGuard guard(h->device);
     cudaStreamSynchronize(h->stream);
+    // graphs that captured the communicator's all-reduce go first: destroying the communicator under them never returns
+    h->drop_graphs();
     if (h->comm) ncclCommDestroy(h->comm);
     h->comm = nullptr;
     h->comm_rank = 0;
